@@ -1,0 +1,125 @@
+/*
+ * vqvae_b200.h -- C ABI of the B200 (sm_100a) VQ-VAE inference hot path.
+ *
+ * The reference (MishaLaskin/vqvae) is pure Python on top of PyTorch and exposes no
+ * FFI of its own; its "plugin API" for this path is the nn.Module
+ * tree models.{vqvae,quantizer,encoder,decoder,residual}.  This header is the
+ * boundary UNDER those modules: each entry point replaces one PyTorch operator call
+ * site of the reference (file:line cited per function, paths under the reference
+ * root).  models/*.py in this repo binds them with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch in practice);
+ *     the library never allocates, frees or retains device memory;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous, make no
+ *     host synchronisation and are CUDA-graph capturable;
+ *   - return value: 0 = success, >0 = cudaError_t, <0 = vqb_status below; no C++
+ *     exception crosses the boundary;
+ *   - activations between layers are NHWC ("pixel rows": (B*H*W, C) row-major); the
+ *     module boundary of the reference is NCHW, so every conv entry point takes an
+ *     explicit layout for its input and output.
+ */
+#ifndef VQVAE_B200_H
+#define VQVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_ABI_VERSION 1
+
+enum vqb_status {
+    VQB_OK = 0,
+    VQB_ERR_BAD_ARG = -1,       /* NULL pointer, non-positive size, bad enum          */
+    VQB_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels implement          */
+    VQB_ERR_WORKSPACE = -3,     /* workspace too small (see *_workspace_bytes)       */
+    VQB_ERR_NO_DEVICE = -4,     /* no sm_100 device / driver                         */
+    VQB_ERR_ALIGNMENT = -5      /* pointer not aligned as documented                 */
+};
+
+enum vqb_layout { VQB_NCHW = 0, VQB_NHWC = 1 };
+
+/* arithmetic of a convolution entry point */
+enum vqb_precision {
+    VQB_FP32 = 0,  /* fp32 FFMA accumulate (CUDA cores): the reference's CPU numerics   */
+    VQB_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (cuDNN's default)     */
+    VQB_BF16 = 2   /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate in TMEM       */
+};
+
+int vqb_abi_version(void);
+const char *vqb_error_string(int code);
+/* SM count and compute capability of the current device. */
+int vqb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- weight packing (once per load_state_dict) --------------------------------
+ * nn.Conv2d weight (Cout,Cin,kh,kw)          encoder.py:29-36, residual.py:20-24,
+ *                                            vqvae.py:16-17
+ * nn.ConvTranspose2d weight (Cin,Cout,kh,kw) decoder.py:28-35   (transposed = 1)
+ * -> tap-major GEMM operand packed[(r*kw+s)*Cin + ci][co], fp32.                */
+int vqb_pack_conv_weight_f32(const float *w, float *packed, int Cout, int Cin, int kh,
+                             int kw, int transposed, void *stream);
+
+/* ---- convolution layers ---------------------------------------------------------
+ * One call = one nn.Conv2d (transposed=0) or nn.ConvTranspose2d (transposed=1)
+ * forward, optionally fused with what follows it in the reference:
+ *   out = act( conv(in) + bias [+ skip] ),  act = ReLU if relu else identity
+ * `skip` (NHWC, shape of out, may be NULL) implements `x + res_block(x)` of
+ * residual.py:27-29; out_layout must be NHWC when skip is given.
+ * w_packed comes from vqb_pack_conv_weight_f32.  Stride-2 transposed convs are run
+ * as 4 sub-pixel phase launches.  Replaces: encoder.py:29-36 (stride 2/2/1, pad 1),
+ * residual.py:20-24, vqvae.py:16-17 (1x1), decoder.py:28-35.                      */
+int vqb_conv2d_f32(const float *in, const float *w_packed, const float *bias,
+                   const float *skip, float *out, int B, int Cin, int H, int W, int Cout,
+                   int kh, int kw, int stride, int pad, int transposed, int in_layout,
+                   int out_layout, int relu, int precision, void *stream);
+
+/* ---- VectorQuantizer.forward, quantizer.py:45-76 --------------------------------
+ * z        (N, D) fp32 pixel rows (= z.permute(0,2,3,1).view(-1, e_dim), :45-46)
+ * codebook (K, D) fp32 embedding.weight (:26)
+ * idx      (N)    int64 min_encoding_indices, first minimum wins, NaN wins (:54)
+ * zq       (N, D) fp32 straight-through value fl(z + fl(e_idx - z)) (:60,:67)
+ * hist     (K)    int32 code counts, ZEROED by the call (column sums of the one-hot
+ *                 of :55-57; feeds the perplexity of :70-71)
+ * sse      (1)    double, sum of fl(e_idx - z)^2, OVERWRITTEN by the call (numerator
+ *                 of the two mean() terms of :63-64)
+ * workspace       vqb_vq_workspace_bytes(N,K,D) bytes, 16-byte aligned
+ * Distances follow the canonical fp32 order documented in DESIGN.md / oracle.c, so
+ * idx and zq are bit-exact against the oracle.                                    */
+size_t vqb_vq_workspace_bytes(int64_t N, int K, int D);
+int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, int D,
+                       int64_t *idx, float *zq, double *sse, int32_t *hist,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* loss = (1+beta)*sse/(N*D) and perplexity = exp(-sum p log(p+1e-10)), p = hist/N,
+ * written as two fp32 device scalars (quantizer.py:63-64, :70-71).  Separate from
+ * the VQ kernel so a batch-sharded caller can all-reduce (hist, sse) in between.  */
+int vqb_vq_finish_f32(const double *sse, const int32_t *hist, int64_t N, int K, int D,
+                      float beta, float *loss, float *perplexity, void *stream);
+
+/* Dense one-hot min_encodings (N,K) fp32 for direct VectorQuantizer.forward callers
+ * (quantizer.py:55-57,76); VQVAE.forward discards it (vqvae.py:34) so it is never
+ * built on that path.                                                             */
+int vqb_onehot_f32(const int64_t *idx, int64_t N, int K, float *onehot, void *stream);
+
+/* z_q rows from indices: matmul(one_hot, embedding.weight) of quantizer.py:60 and of
+ * the notebook's generate_samples (visualization.ipynb cell 13) as a row gather.
+ * Indices outside [0, K) are clamped to the nearest valid row.                    */
+int vqb_gather_rows_f32(const int64_t *idx, const float *codebook, int64_t N, int K, int D,
+                        float *rows, void *stream);
+
+/* In-place ReLU over n floats: the nn.ReLU(True) of residual.py:19, which mutates
+ * the caller's tensor when a ResidualLayer is called directly.         */
+int vqb_relu_f32(float *x, int64_t n, void *stream);
+
+/* ---- layout changes at the module boundary (quantizer.py:45, :74) ---------------- */
+int vqb_nchw_to_nhwc_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);
+int vqb_nhwc_to_nchw_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQVAE_B200_H */

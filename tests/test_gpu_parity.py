@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed
+golden vectors of the unmodified reference.  Needs a B200: run with ``-m gpu``.
+
+Bars: integer / index outputs bit-exact; fp32 z_q bitwise at the VQ boundary; fp32
+conv outputs within 2e-6 absolute of the double-accumulated oracle at |y| = O(1e-1)
+(fp32 FFMA path); scalars within 2e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref
+from tests.helpers import (MODEL_CASES, VQ_CASES, build_model, load_golden, make_vq_inputs,
+                           model_case_inputs)
+
+pytestmark = pytest.mark.gpu
+
+CONV_ATOL = 2e-6     # fp32 FFMA vs double-accumulated oracle, activations O(0.1..1)
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# --------------------------------------------------------------------------- VQ kernel
+@pytest.mark.parametrize("name", sorted(VQ_CASES))
+def test_vq_kernel_bit_exact_vs_oracle_and_reference(name):
+    from vqvae_b200 import ops
+    g = load_golden(name)
+    z, E = make_vq_inputs(**g["case"])
+    B, D, H, W = z.shape
+    rows = np.ascontiguousarray(z.transpose(0, 2, 3, 1)).reshape(-1, D)
+    o = cref.vq_rows(rows, E)
+    idx, zq, sse, hist = ops.vq_forward(_cuda(rows), _cuda(E))
+    loss, perp = ops.vq_finish(sse, hist, rows.shape[0], E.shape[0], D, 0.25)
+    torch.cuda.synchronize()
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), o["idx"])                       # vs oracle
+    assert np.array_equal(idx.cpu().numpy(), g["idx"].ravel())               # vs reference
+    assert np.array_equal(zq.cpu().numpy(), o["zq"], equal_nan=True)         # bitwise
+    assert np.array_equal(hist.cpu().numpy(), g["hist"])
+    np.testing.assert_allclose(sse.item(), o["sse"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(perp.item(), g["perplexity"], rtol=2e-5)
+
+
+def test_vq_module_five_tuple_matches_reference():
+    from models.quantizer import VectorQuantizer
+    g = load_golden("vq_k512_d64")
+    z, E = make_vq_inputs(**g["case"])
+    vq = VectorQuantizer(512, 64, 0.25)
+    vq.embedding.weight.data.copy_(torch.from_numpy(E))
+    vq = vq.cuda()
+    loss, z_q, perp, onehot, idx = vq(_cuda(z))
+    assert idx.shape == (z.shape[0] * z.shape[2] * z.shape[3], 1) and idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert z_q.shape == z.shape and z_q.is_contiguous()
+    assert np.array_equal(z_q.cpu().numpy(), g["z_q"])
+    assert onehot.shape == (idx.shape[0], 512) and onehot.dtype == torch.float32
+    oh = onehot.cpu().numpy()
+    assert np.array_equal(oh.argmax(1), g["idx"].ravel()) and np.all(oh.sum(1) == 1.0)
+    assert np.array_equal(oh.sum(0).astype(np.int32), g["hist"])
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(perp.item(), g["perplexity"], rtol=2e-5)
+
+
+def test_vq_rejects_wrong_channel_count_and_cpu_tensor():
+    from models.quantizer import VectorQuantizer
+    vq = VectorQuantizer(16, 8, 0.25).cuda()
+    with pytest.raises(RuntimeError):
+        vq(torch.zeros(1, 4, 2, 2, device="cuda"))
+    with pytest.raises(RuntimeError):
+        vq(torch.zeros(1, 8, 2, 2))          # CPU tensor: no CPU fallback
+
+
+@pytest.mark.parametrize("N,K,D", [(1, 1, 4), (63, 65, 12), (64, 64, 64), (65, 129, 32), (1000, 513, 256)])
+def test_vq_ragged_sizes(N, K, D):
+    from vqvae_b200 import ops
+    rng = np.random.RandomState(N + K + D)
+    rows = rng.standard_normal((N, D)).astype(np.float32)
+    E = rng.standard_normal((K, D)).astype(np.float32)
+    o = cref.vq_rows(rows, E)
+    idx, zq, sse, hist = ops.vq_forward(_cuda(rows), _cuda(E))
+    assert np.array_equal(idx.cpu().numpy(), o["idx"])
+    assert np.array_equal(zq.cpu().numpy(), o["zq"])
+    assert np.array_equal(hist.cpu().numpy(), o["hist"])
+
+
+# --------------------------------------------------------------------------- conv layers
+def _conv_case(rng, B, Cin, H, W, Cout, k, stride, pad, transposed, in_layout, out_layout, relu, skip):
+    from vqvae_b200 import ops
+    from vqvae_b200._lib import NCHW
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+    w = (rng.standard_normal(wshape) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    ref = cref.conv_transpose2d(x, w, b, stride, pad) if transposed else cref.conv2d(x, w, b, stride, pad)
+    sk = None
+    if skip:
+        sk = rng.standard_normal(ref.shape).astype(np.float32)
+        ref = ref + sk
+    if relu:
+        ref = np.maximum(ref, 0)
+    xin = x if in_layout == NCHW else np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+    wp = ops.pack_conv_weight(_cuda(w), transposed)
+    y = ops.conv2d(_cuda(xin), wp, _cuda(b), B=B, Cin=Cin, H=H, W=W, Cout=Cout, kh=k, kw=k,
+                   stride=stride, pad=pad, transposed=transposed, in_layout=in_layout,
+                   out_layout=out_layout, relu=relu,
+                   skip=_cuda(np.ascontiguousarray(sk.transpose(0, 2, 3, 1))) if skip else None)
+    y = y.cpu().numpy()
+    if out_layout != NCHW:
+        y = y.transpose(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    np.testing.assert_allclose(y, ref, atol=5e-6, rtol=1e-5)
+
+
+CONV_CASES = [
+    # B, Cin, H,  W,  Cout, k, s, p, transposed, in, out, relu, skip     (reference layer)
+    (2, 3, 32, 32, 64, 4, 2, 1, False, 0, 1, True, False),     # encoder.py:29-31, NCHW in
+    (2, 64, 16, 16, 128, 4, 2, 1, False, 1, 1, True, False),   # encoder.py:32-34
+    (2, 128, 8, 8, 128, 3, 1, 1, False, 1, 1, False, False),   # encoder.py:35-36
+    (2, 128, 8, 8, 32, 3, 1, 1, False, 1, 1, True, False),     # residual.py:20-22
+    (2, 32, 8, 8, 128, 1, 1, 0, False, 1, 1, True, True),      # residual.py:23-24,28 (+skip)
+    (2, 128, 8, 8, 64, 1, 1, 0, False, 1, 1, False, False),    # vqvae.py:16-17
+    (2, 128, 8, 8, 64, 1, 1, 0, False, 0, 0, False, False),    # same, NCHW in/out (piecewise API)
+    (2, 64, 8, 8, 128, 3, 1, 1, True, 1, 1, False, False),     # decoder.py:28-29
+    (2, 128, 8, 8, 64, 4, 2, 1, True, 1, 1, True, False),      # decoder.py:31-33
+    (2, 64, 16, 16, 3, 4, 2, 1, True, 1, 0, False, False),     # decoder.py:34-35, NCHW out
+    (3, 5, 7, 9, 6, 3, 1, 1, False, 0, 0, False, False),       # odd everything
+    (1, 8, 5, 6, 10, 4, 2, 1, True, 1, 1, True, False),        # odd transposed
+    (1, 12, 6, 5, 2, 3, 1, 1, True, 1, 0, False, False),       # small-Cout kernel, k3
+    (2, 6, 9, 7, 3, 4, 2, 1, True, 0, 0, False, False),        # Cout=3 from NCHW input
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_layers_vs_oracle(case):
+    rng = np.random.RandomState(abs(hash(case)) % (2 ** 31))
+    _conv_case(rng, *case)
+
+
+# --------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize("name", sorted(MODEL_CASES))
+def test_vqvae_forward_vs_reference_golden(name):
+    g = load_golden(name)
+    hp, sd, x = model_case_inputs(g["case"])
+    m = build_model(hp, sd)
+    xc = _cuda(x)
+    # piecewise API the notebook uses (visualization.ipynb cell 1 `reconstruct`)
+    z_e = m.pre_quantization_conv(m.encoder(xc.clone()))
+    np.testing.assert_allclose(z_e.cpu().numpy(), g["z_e"], atol=CONV_ATOL, rtol=0)
+    # VQ boundary: the reference's own z_e in -> bit-exact indices, bitwise z_q
+    loss_b, zq_b, perp_b, _, idx_b = m.vector_quantization(_cuda(g["z_e"]))
+    assert np.array_equal(idx_b.cpu().numpy(), g["idx"])
+    assert np.array_equal(zq_b.cpu().numpy(), g["z_q"])
+    np.testing.assert_allclose(loss_b.item(), g["loss"], rtol=1e-5)
+    np.testing.assert_allclose(perp_b.item(), g["perplexity"], rtol=2e-5)
+    # decoder on the reference's z_q
+    xh_b = m.decoder(_cuda(g["z_q"]))
+    np.testing.assert_allclose(xh_b.cpu().numpy(), g["x_hat"], atol=CONV_ATOL, rtol=0)
+    # fused forward
+    loss, x_hat, perp = m(xc)
+    idx = m.last_min_encoding_indices.cpu().numpy()
+    mism = int((idx != g["idx"]).sum())
+    if mism:
+        # an end-to-end flip is only acceptable on a provable near-tie of the oracle's
+        # fp64 distances computed from OUR z_e
+        rows = z_e.permute(0, 2, 3, 1).reshape(-1, hp["embedding_dim"]).double().cpu().numpy()
+        E = sd["vector_quantization.embedding.weight"].astype(np.float64)
+        d = (rows ** 2).sum(1, keepdims=True) + (E ** 2).sum(1) - 2 * rows @ E.T
+        bad = np.nonzero((idx != g["idx"]).ravel())[0]
+        gap = np.abs(d[bad, idx.ravel()[bad]] - d[bad, g["idx"].ravel()[bad]])
+        assert np.all(gap <= 4 * np.spacing(np.float32(np.abs(d[bad]).max()))), (mism, gap)
+    assert mism <= max(1, idx.size // 1000)
+    if mism == 0:
+        np.testing.assert_allclose(x_hat.cpu().numpy(), g["x_hat"], atol=CONV_ATOL, rtol=0)
+        np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+        np.testing.assert_allclose(perp.item(), g["perplexity"], rtol=2e-5)
+    assert x_hat.shape == x.shape and x_hat.is_contiguous() and x_hat.dtype == torch.float32
+
+
+def test_encode_decode_entry_points_match_forward():
+    g = load_golden("cifar_spread")
+    hp, sd, x = model_case_inputs(g["case"])
+    m = build_model(hp, sd)
+    xc = _cuda(x)
+    _, x_hat, _ = m(xc)
+    idx = m.encode(xc)
+    assert torch.equal(idx, m.last_min_encoding_indices)
+    x_dec = m.decode(idx, (x.shape[2] // 4, x.shape[3] // 4))
+    # decode() feeds E[idx]; forward feeds z + (E[idx] - z): differ by <= 1 ulp of z_q (Q4)
+    np.testing.assert_allclose(x_dec.cpu().numpy(), x_hat.cpu().numpy(), atol=1e-6, rtol=0)
+
+
+def test_residual_layer_in_place_relu_and_shared_weights():
+    """the caller's tensor is ReLU'd in place; the stack shares one layer."""
+    from models.residual import ResidualLayer, ResidualStack
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal((2, 16, 5, 6)).astype(np.float32)
+    layer = ResidualLayer(16, 16, 8).cuda()
+    w1 = layer.res_block[1].weight.detach().cpu().numpy()
+    w2 = layer.res_block[3].weight.detach().cpu().numpy()
+    xc = _cuda(x)
+    y = layer(xc)
+    r = np.maximum(x, 0)
+    ref = r + cref.conv2d(np.maximum(cref.conv2d(r, w1, None, 1, 1), 0), w2, None, 1, 0)
+    np.testing.assert_allclose(y.cpu().numpy(), ref, atol=5e-6)
+    assert np.array_equal(xc.cpu().numpy(), r)            # mutated like nn.ReLU(True)
+    st = ResidualStack(16, 16, 8, 3).cuda()
+    assert st.stack[0] is st.stack[1] is st.stack[2]
+    w1 = st.stack[0].res_block[1].weight.detach().cpu().numpy()
+    w2 = st.stack[0].res_block[3].weight.detach().cpu().numpy()
+    y = st(_cuda(x))
+    np.testing.assert_allclose(y.cpu().numpy(), cref.residual_stack(x, w1, w2, 3), atol=1e-5)
+
+
+def test_verbose_path_prints_and_asserts(capsys):
+    g = load_golden("no_res")
+    hp, sd, x = model_case_inputs(g["case"])
+    m = build_model(hp, sd)
+    with pytest.raises(AssertionError):
+        m(_cuda(x), verbose=True)
+    out = capsys.readouterr().out
+    assert "original data shape" in out and "encoded data shape" in out and "recon data shape" in out
+
+
+# ------------------------------------------------------- full-size properties (cfg2)
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 (B=256, 32x32, K=512, D=64): size-independent properties."""
+    from oracle.weights import make_images, make_state_dict
+    hp = dict(h_dim=128, res_h_dim=32, n_res_layers=2, n_embeddings=512, embedding_dim=64)
+    sd = make_state_dict(seed=0, codebook="normal", codebook_scale=0.05, **hp)
+    m = build_model(hp, sd)
+    x = _cuda(make_images(256, 32, seed=1))
+    loss, x_hat, perp = m(x)
+    idx = m.last_min_encoding_indices
+    N = 256 * 8 * 8
+    assert idx.shape == (N, 1) and int(idx.min()) >= 0 and int(idx.max()) < 512
+    # batch independence: a slice of the batch gives the slice of the outputs, bitwise
+    loss_h, x_hat_h, _ = m(x[64:128].contiguous())
+    assert torch.equal(x_hat_h, x_hat[64:128])
+    assert torch.equal(m.last_min_encoding_indices, idx.view(256, 64)[64:128].reshape(-1, 1))
+    # idempotence: quantising z_q again returns the same codes
+    z_e = m.pre_quantization_conv(m.encoder(x.clone()))
+    l1, zq1, p1, _, i1 = m.vector_quantization(z_e)
+    assert torch.equal(i1, idx)
+    l2, zq2, p2, _, i2 = m.vector_quantization(zq1)
+    assert torch.equal(i2, i1)
+    # straight-through value is within 1 ulp of the gathered code (Q4)
+    E = m.vector_quantization.embedding.weight
+    e = E[i1.view(-1)].view(256, 8, 8, 64).permute(0, 3, 1, 2)
+    assert float((zq1 - e).abs().max()) <= 1.5e-8 * 4
+    # loss = (1+beta) * mse(e, z_e) and perplexity from the histogram of idx
+    mse = ((e - z_e).double() ** 2).mean().item()
+    np.testing.assert_allclose(loss.item(), 1.25 * mse, rtol=1e-5)
+    p = torch.bincount(idx.view(-1), minlength=512).double() / N
+    np.testing.assert_allclose(perp.item(), float(torch.exp(-(p * torch.log(p + 1e-10)).sum())), rtol=1e-5)
+    # oracle spot check of the first 4 images at full depth
+    o = cref.vqvae_forward(x[:4].cpu().numpy(), sd, 2)
+    np.testing.assert_allclose(x_hat[:4].cpu().numpy(), o["x_hat"], atol=CONV_ATOL, rtol=0)
+    assert np.array_equal(idx.view(256, 64)[:4].reshape(-1, 1).cpu().numpy(), o["idx"])

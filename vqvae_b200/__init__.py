@@ -1,0 +1,11 @@
+"""vqvae_b200 -- B200-native (sm_100a) VQ-VAE inference hot path.
+
+Hand-written CUDA kernels behind a C ABI (include/vqvae_b200.h), plus the host-side
+mirror of the reference's nn.Module API (vqvae_b200.modules; re-exported by the
+top-level ``models`` package so ``from models.vqvae import VQVAE`` drops in).
+"""
+from .modules import (Decoder, Encoder, ResidualLayer, ResidualStack, VectorQuantizer, VQVAE,  # noqa: F401
+                      get_precision, precision, set_precision)
+
+__all__ = ["VQVAE", "VectorQuantizer", "Encoder", "Decoder", "ResidualLayer", "ResidualStack",
+           "set_precision", "get_precision", "precision"]

@@ -1,0 +1,58 @@
+"""ctypes binding of include/vqvae_b200.h (the C-ABI boundary).
+
+The library is built in-tree by vqvae_b200/build.py (nvcc, sm_100a).  Loading never
+falls back to anything: if the shared object is missing the import of the product
+fails loudly.
+"""
+import ctypes as C
+import os
+
+from .build import LIB, build
+
+_lib = None
+
+# enums of include/vqvae_b200.h
+NCHW, NHWC = 0, 1
+FP32, TF32, BF16 = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "bf16": BF16}
+
+_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); mirrors the header one to one (tests check this)
+SIGNATURES = {
+    "vqb_abi_version": (_i, []),
+    "vqb_error_string": (C.c_char_p, [_i]),
+    "vqb_device_info": (_i, [C.POINTER(_i)] * 3),
+    "vqb_pack_conv_weight_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "vqb_conv2d_f32": (_i, [_vp] * 5 + [_i] * 14 + [_vp]),
+    "vqb_vq_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "vqb_vq_forward_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vqb_vq_finish_f32": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp]),
+    "vqb_onehot_f32": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "vqb_gather_rows_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vqb_nchw_to_nhwc_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vqb_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "vqb_relu_f32": (_i, [_vp, _i64, _vp]),
+}
+
+
+def lib():
+    """The loaded C-ABI library (built on first use if the .so is absent/stale)."""
+    global _lib
+    if _lib is None:
+        path = LIB if os.path.exists(LIB) and os.environ.get("VQB_NO_REBUILD") else build()
+        handle = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if handle.vqb_abi_version() != 1:
+            raise RuntimeError("libvqvae_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().vqb_error_string(int(code)).decode()
+        raise RuntimeError(f"{what}: {msg} (code {code})")

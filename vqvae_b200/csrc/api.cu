@@ -1,0 +1,133 @@
+// api.cu -- the extern "C" boundary declared in include/vqvae_b200.h.
+#include "common.cuh"
+
+size_t vq_exact_workspace_bytes(int K);
+int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq,
+                    double *sse, int *hist, void *ws, cudaStream_t s);
+
+extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
+
+extern "C" const char *vqb_error_string(int code) {
+    switch (code) {
+        case VQB_OK: return "success";
+        case VQB_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or bad enum)";
+        case VQB_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernels";
+        case VQB_ERR_WORKSPACE: return "workspace too small";
+        case VQB_ERR_NO_DEVICE: return "no CUDA device";
+        case VQB_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown vqb error";
+    }
+}
+
+extern "C" int vqb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return VQB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return VQB_ERR_NO_DEVICE;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+static void set_strides(int layout, int C, int H, int W, long long &sn, long long &sh, long long &sw,
+                        long long &sc) {
+    if (layout == VQB_NCHW) {
+        sn = (long long)C * H * W; sc = (long long)H * W; sh = W; sw = 1;
+    } else {
+        sn = (long long)H * W * C; sh = (long long)W * C; sw = C; sc = 1;
+    }
+}
+
+extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const float *bias, const float *skip,
+                              float *out, int B, int Cin, int H, int W, int Cout, int kh, int kw, int stride,
+                              int pad, int transposed, int in_layout, int out_layout, int relu, int precision,
+                              void *stream) {
+    if (!in || !w_packed || !out) return VQB_ERR_BAD_ARG;
+    if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+        return VQB_ERR_BAD_ARG;
+    if ((in_layout != VQB_NCHW && in_layout != VQB_NHWC) || (out_layout != VQB_NCHW && out_layout != VQB_NHWC))
+        return VQB_ERR_BAD_ARG;
+    if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
+    if (skip && out_layout != VQB_NHWC) return VQB_ERR_BAD_ARG;
+    if (kh * kw > VQB_MAX_TAPS) return VQB_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const int OH = transposed ? (H - 1) * stride - 2 * pad + kh : (H + 2 * pad - kh) / stride + 1;
+    const int OW = transposed ? (W - 1) * stride - 2 * pad + kw : (W + 2 * pad - kw) / stride + 1;
+    if (OH <= 0 || OW <= 0) return VQB_ERR_BAD_ARG;
+
+    ConvLaunch p;
+    p.in = in; p.w = w_packed; p.bias = bias; p.skip = skip; p.out = out;
+    p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
+    set_strides(in_layout, Cin, H, W, p.in_sn, p.in_sh, p.in_sw, p.in_sc);
+    set_strides(out_layout, Cout, OH, OW, p.out_sn, p.out_sh, p.out_sw, p.out_sc);
+    const bool small = (Cout <= 4);
+
+    if (!transposed || stride == 1) {
+        p.OHg = OH; p.OWg = OW;
+        p.in_step = transposed ? 1 : stride;
+        p.out_step = 1; p.out_py = 0; p.out_px = 0;
+        p.ntaps = kh * kw;
+        for (int r = 0; r < kh; ++r)
+            for (int c = 0; c < kw; ++c) {
+                const int t = r * kw + c;
+                p.tap_w[t] = t;
+                p.tap_dy[t] = transposed ? pad - r : r - pad;
+                p.tap_dx[t] = transposed ? pad - c : c - pad;
+            }
+        return small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
+    }
+    // stride-s transposed conv: s*s sub-pixel phases, each a stride-1 gather conv
+    // over the taps whose parity matches (decoder.py:31-35).
+    p.in_step = 1; p.out_step = stride;
+    for (int py = 0; py < stride; ++py)
+        for (int px = 0; px < stride; ++px) {
+            p.out_py = py; p.out_px = px;
+            p.OHg = (OH - py + stride - 1) / stride;
+            p.OWg = (OW - px + stride - 1) / stride;
+            if (p.OHg <= 0 || p.OWg <= 0) continue;
+            int nt = 0;
+            for (int r = 0; r < kh; ++r) {
+                if ((py + pad - r) % stride != 0) continue;
+                for (int c = 0; c < kw; ++c) {
+                    if ((px + pad - c) % stride != 0) continue;
+                    p.tap_w[nt] = r * kw + c;
+                    p.tap_dy[nt] = (py + pad - r) / stride;
+                    p.tap_dx[nt] = (px + pad - c) / stride;
+                    ++nt;
+                }
+            }
+            p.ntaps = nt;
+            int rc;
+            if (nt == 0) {
+                // a phase no tap reaches still gets bias/skip/activation
+                p.ntaps = 0;
+            }
+            rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
+            if (rc != 0) return rc;
+        }
+    return 0;
+}
+
+extern "C" size_t vqb_vq_workspace_bytes(int64_t N, int K, int D) {
+    (void)N; (void)D;
+    if (K <= 0) return 0;
+    return vq_exact_workspace_bytes(K);
+}
+
+extern "C" int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
+                                  float *zq, double *sse, int32_t *hist, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    if (!z || !codebook || !idx || !zq || !sse || !hist || !workspace) return VQB_ERR_BAD_ARG;
+    if (N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
+    if (D % 4 != 0) return VQB_ERR_UNSUPPORTED;
+    if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(codebook) |
+                         reinterpret_cast<uintptr_t>(zq) | reinterpret_cast<uintptr_t>(workspace);
+    if (al & 15) return VQB_ERR_ALIGNMENT;
+    return launch_vq_exact(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
+                           (cudaStream_t)stream);
+}

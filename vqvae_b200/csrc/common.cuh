@@ -1,0 +1,33 @@
+// common.cuh -- shared declarations of the sm_100a VQ-VAE kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vqvae_b200.h"
+
+#define VQB_MAX_TAPS 16
+
+// One launch of the generalised gather-form convolution
+//   out[n, gy*out_step+out_py, gx*out_step+out_px, co] =
+//       act( bias[co] + skip + sum_{t<ntaps, ci} in[n, gy*in_step+dy[t], gx*in_step+dx[t], ci]
+//                                                * w[tap_w[t]*Cin + ci][co] )
+// which covers nn.Conv2d (in_step = stride, out_step = 1, dy = r - pad), stride-1
+// nn.ConvTranspose2d (dy = pad - r) and one sub-pixel phase of a stride-2
+// nn.ConvTranspose2d (in_step = 1, out_step = 2, taps of matching parity).
+struct ConvLaunch {
+    const float *in, *w, *bias, *skip;
+    float *out;
+    int B, Cin, H, W, Cout;
+    int OHg, OWg;                 // output grid of this launch
+    int in_step, out_step, out_py, out_px;
+    int ntaps;
+    int tap_w[VQB_MAX_TAPS], tap_dy[VQB_MAX_TAPS], tap_dx[VQB_MAX_TAPS];
+    long long in_sn, in_sh, in_sw, in_sc;      // element strides of `in`
+    long long out_sn, out_sh, out_sw, out_sc;  // element strides of `out` (and `skip`)
+    int relu;
+};
+
+int launch_conv_ffma(const ConvLaunch &p, cudaStream_t s);
+int launch_conv_small_cout(const ConvLaunch &p, cudaStream_t s);
+
+static inline int vqb_cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

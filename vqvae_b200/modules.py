@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's nn.Module API for the VQVAE.forward hot path.
+
+Same class names, constructor signatures, attribute names and state-dict keys as
+MishaLaskin/vqvae ``models/{vqvae,quantizer,encoder,decoder,residual}.py``,
+so ``from models.vqvae import VQVAE`` keeps working (the top-level ``models`` package
+re-exports these classes).  The nn.Conv2d / nn.ConvTranspose2d / nn.Embedding children
+are kept ONLY as parameter containers (identical init order => identical weights under
+the same torch seed, identical ``state_dict()``); their own ``forward`` is never used.
+Every ``forward`` here launches the hand-written sm_100a kernels through the C ABI
+(``include/vqvae_b200.h``).  Inference only: outputs carry no autograd graph.
+
+Reference semantics reproduced on purpose:
+  Q1  ResidualStack applies ONE shared ResidualLayer n times (residual.py:44-45)
+  Q2  the in-place ReLU makes a layer relu(x) + f(relu(x)) and mutates the caller's x
+  Q3  final F.relu after the stack; no activation after encoder conv 4 / decoder convT 0
+  Q4  z_q is bitwise z + (e - z)
+  Q7  the dense one-hot is built only for direct VectorQuantizer.forward callers
+  Q8  verbose=True prints three shapes and then ``assert False``
+"""
+import contextlib
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import NCHW, NHWC, PRECISIONS
+
+_PRECISION = {"value": "fp32"}
+
+
+def set_precision(name: str):
+    """Arithmetic of the convolution layers: "fp32" (FFMA, the reference's CPU numerics;
+    default), "tf32" or "bf16" (tcgen05 tensor cores, fp32 accumulation)."""
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+    _PRECISION["value"] = name
+
+
+def get_precision() -> str:
+    return _PRECISION["value"]
+
+
+@contextlib.contextmanager
+def precision(name: str):
+    old = get_precision()
+    set_precision(name)
+    try:
+        yield
+    finally:
+        set_precision(old)
+
+
+class _PackedWeights:
+    """Cache of tap-major packed conv weights, refreshed when a parameter changes
+    (load_state_dict / .to() / in-place edits bump ``_version`` or move the storage)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, param, transposed):
+        key = id(param)
+        tag = (param._version, param.data_ptr(), str(param.device))
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.pack_conv_weight(param, transposed))
+            self._cache[key] = hit
+        return hit[1]
+
+
+_PACKED = _PackedWeights()
+
+
+def _bias(conv):
+    if conv.bias is None:
+        return None
+    b = conv.bias.detach()
+    return b if b.dtype == torch.float32 else b.float()
+
+
+def _run_conv(conv, x, B, H, W, *, in_layout=NHWC, out_layout=NHWC, relu=False, skip=None):
+    """Forward of one nn.Conv2d / nn.ConvTranspose2d container through vqb_conv2d_f32."""
+    transposed = isinstance(conv, nn.ConvTranspose2d)
+    kh, kw = conv.kernel_size
+    stride, pad = conv.stride[0], conv.padding[0]
+    w = _PACKED.get(conv.weight, transposed)
+    return ops.conv2d(x, w, _bias(conv), B=B, Cin=conv.in_channels, H=H, W=W, Cout=conv.out_channels,
+                      kh=kh, kw=kw, stride=stride, pad=pad, transposed=transposed, in_layout=in_layout,
+                      out_layout=out_layout, relu=relu, skip=skip,
+                      precision=PRECISIONS[get_precision()])
+
+
+def _prep_input(x, channels, what):
+    if x.dim() != 4:
+        raise RuntimeError(f"{what}: expected a 4-D (B,C,H,W) tensor, got {tuple(x.shape)}")
+    if x.shape[1] != channels:
+        raise RuntimeError(f"{what}: expected {channels} input channels, got {x.shape[1]}")
+    ops._require_cuda(x, what + " input")
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x if x.is_contiguous() else x.contiguous()
+
+
+class ResidualLayer(nn.Module):
+    """One residual layer (reference models/residual.py:8-29)."""
+
+    def __init__(self, in_dim, h_dim, res_h_dim):
+        super().__init__()
+        self.res_block = nn.Sequential(
+            nn.ReLU(True),
+            nn.Conv2d(in_dim, res_h_dim, kernel_size=3, stride=1, padding=1, bias=False),
+            nn.ReLU(True),
+            nn.Conv2d(res_h_dim, h_dim, kernel_size=1, stride=1, bias=False),
+        )
+
+    def _apply_nhwc(self, r, B, H, W, relu_out):
+        """r = relu(x) in NHWC.  Returns r + W2.relu(W1 (*) r), optionally ReLU'd
+        (the next consumer always applies ReLU first, residual.py:19,50)."""
+        h = _run_conv(self.res_block[1], r, B, H, W, relu=True)
+        return _run_conv(self.res_block[3], h, B, H, W, relu=relu_out, skip=r)
+
+    def forward(self, x):
+        xin = x
+        x = _prep_input(x, self.res_block[1].in_channels, "ResidualLayer")
+        B, _, H, W = x.shape
+        # Q2: nn.ReLU(True) rewrites the caller's tensor before the sum is formed.
+        if xin.is_contiguous() and xin.dtype == torch.float32 and not xin.requires_grad:
+            ops.relu_(xin)
+            x = xin
+        else:
+            x = ops.relu_(x.clone())
+        r = ops.nchw_to_nhwc(x)
+        return ops.nhwc_to_nchw(self._apply_nhwc(r, B, H, W, relu_out=False))
+
+
+class ResidualStack(nn.Module):
+    """n applications of ONE shared ResidualLayer, then ReLU (models/residual.py:32-51)."""
+
+    def __init__(self, in_dim, h_dim, res_h_dim, n_res_layers):
+        super().__init__()
+        self.n_res_layers = n_res_layers
+        self.stack = nn.ModuleList([ResidualLayer(in_dim, h_dim, res_h_dim)] * n_res_layers)
+
+    def _apply_nhwc(self, r, B, H, W):
+        """r = relu(stack input), NHWC.  Output = the stack's result (post F.relu)."""
+        for layer in self.stack:
+            r = layer._apply_nhwc(r, B, H, W, relu_out=True)
+        return r
+
+    def forward(self, x):
+        ch = self.stack[0].res_block[1].in_channels if len(self.stack) else x.shape[1]
+        xin = x
+        x = _prep_input(x, ch, "ResidualStack")
+        B, _, H, W = x.shape
+        if len(self.stack) and xin.is_contiguous() and xin.dtype == torch.float32 \
+                and not xin.requires_grad:
+            ops.relu_(xin)      # side effect of the first layer's in-place ReLU (Q2)
+            x = xin
+        else:
+            x = ops.relu_(x.clone())
+        return ops.nhwc_to_nchw(self._apply_nhwc(ops.nchw_to_nhwc(x), B, H, W))
+
+
+class Encoder(nn.Module):
+    """q_theta(z|x): models/encoder.py:9-43."""
+
+    def __init__(self, in_dim, h_dim, n_res_layers, res_h_dim):
+        super().__init__()
+        kernel, stride = 4, 2
+        self.conv_stack = nn.Sequential(
+            nn.Conv2d(in_dim, h_dim // 2, kernel_size=kernel, stride=stride, padding=1),
+            nn.ReLU(),
+            nn.Conv2d(h_dim // 2, h_dim, kernel_size=kernel, stride=stride, padding=1),
+            nn.ReLU(),
+            nn.Conv2d(h_dim, h_dim, kernel_size=kernel - 1, stride=stride - 1, padding=1),
+            ResidualStack(h_dim, h_dim, res_h_dim, n_res_layers),
+        )
+
+    def _forward_nhwc(self, x):
+        """x: prepared NCHW fp32 CUDA tensor -> (NHWC activation, B, H, W)."""
+        B, _, H, W = x.shape
+        cs = self.conv_stack
+        h = _run_conv(cs[0], x, B, H, W, in_layout=NCHW, relu=True)
+        H, W = h.shape[1], h.shape[2]
+        h = _run_conv(cs[2], h, B, H, W, relu=True)
+        H, W = h.shape[1], h.shape[2]
+        # the only consumer of conv 4 is the stack, whose first op is ReLU (or, with an
+        # empty stack, its final F.relu): fold that ReLU into this epilogue (Q2/Q3).
+        h = _run_conv(cs[4], h, B, H, W, relu=True)
+        h = cs[5]._apply_nhwc(h, B, H, W)
+        return h, B, H, W
+
+    def forward(self, x):
+        x = _prep_input(x, self.conv_stack[0].in_channels, "Encoder")
+        h, _, _, _ = self._forward_nhwc(x)
+        return ops.nhwc_to_nchw(h)
+
+
+class Decoder(nn.Module):
+    """p_phi(x|z): models/decoder.py:9-39."""
+
+    def __init__(self, in_dim, h_dim, n_res_layers, res_h_dim):
+        super().__init__()
+        kernel, stride = 4, 2
+        self.inverse_conv_stack = nn.Sequential(
+            nn.ConvTranspose2d(in_dim, h_dim, kernel_size=kernel - 1, stride=stride - 1, padding=1),
+            ResidualStack(h_dim, h_dim, res_h_dim, n_res_layers),
+            nn.ConvTranspose2d(h_dim, h_dim // 2, kernel_size=kernel, stride=stride, padding=1),
+            nn.ReLU(),
+            nn.ConvTranspose2d(h_dim // 2, 3, kernel_size=kernel, stride=stride, padding=1),
+        )
+
+    def _forward_from_nhwc(self, z, B, H, W):
+        """z: NHWC (B,H,W,in_dim) -> x_hat NCHW."""
+        ics = self.inverse_conv_stack
+        h = _run_conv(ics[0], z, B, H, W, relu=True)     # ReLU of the stack folded in (Q2/Q3)
+        H, W = h.shape[1], h.shape[2]
+        h = ics[1]._apply_nhwc(h, B, H, W)
+        h = _run_conv(ics[2], h, B, H, W, relu=True)
+        H, W = h.shape[1], h.shape[2]
+        return _run_conv(ics[4], h, B, H, W, out_layout=NCHW)
+
+    def forward(self, x):
+        x = _prep_input(x, self.inverse_conv_stack[0].in_channels, "Decoder")
+        B, _, H, W = x.shape
+        return self._forward_from_nhwc(ops.nchw_to_nhwc(x), B, H, W)
+
+
+class VectorQuantizer(nn.Module):
+    """Discretisation bottleneck: models/quantizer.py:10-76."""
+
+    def __init__(self, n_e, e_dim, beta):
+        super().__init__()
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.embedding = nn.Embedding(self.n_e, self.e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)
+
+    def _codebook(self):
+        w = self.embedding.weight.detach()
+        if w.dtype != torch.float32:
+            w = w.float()
+        return w if w.is_contiguous() else w.contiguous()
+
+    def _quantize_rows(self, rows, group=None):
+        """rows (N, e_dim) fp32 CUDA -> (loss, zq_rows, perplexity, idx (N,))."""
+        idx, zq, sse, hist = ops.vq_forward(rows, self._codebook())
+        n_total = rows.shape[0]
+        if group is not None and torch.distributed.get_world_size(group) > 1:
+            # batch-sharded forward: loss and perplexity are the only
+            # cross-sample quantities; reduce their sufficient statistics.
+            # One tiny all-reduce of [hist (K) | sse] as float64 (counts are exact in
+            # f64).  Shards are equal-sized (contiguous batch split), so the global row
+            # count is n_local * world_size and no host sync is needed.
+            stats = torch.cat([hist.double(), sse])
+            torch.distributed.all_reduce(stats, group=group)
+            hist = stats[:-1].round().to(torch.int32)
+            sse = stats[-1:].contiguous()
+            n_total = n_total * torch.distributed.get_world_size(group)
+        loss, perp = ops.vq_finish(sse, hist, n_total, self.n_e, self.e_dim, self.beta)
+        return loss, zq, perp, idx
+
+    def forward(self, z):
+        z = _prep_input(z, self.e_dim, "VectorQuantizer")   # Q11: channels must equal e_dim
+        B, D, H, W = z.shape
+        rows = ops.nchw_to_nhwc(z).view(-1, D)                              # quantizer.py:45-46
+        loss, zq, perp, idx = self._quantize_rows(rows)
+        z_q = ops.nhwc_to_nchw(zq.view(B, H, W, D))                         # :74
+        min_encoding_indices = idx.view(-1, 1)                              # :54
+        min_encodings = ops.onehot(idx, self.n_e)                           # :55-57 (Q7)
+        return loss, z_q, perp, min_encodings, min_encoding_indices
+
+
+class _PointwiseConv2d(nn.Conv2d):
+    """nn.Conv2d container whose forward runs vqb_conv2d_f32 (vqvae.py:16-17,33)."""
+
+    def forward(self, x):
+        x = _prep_input(x, self.in_channels, "pre_quantization_conv")
+        B, _, H, W = x.shape
+        return _run_conv(self, x, B, H, W, in_layout=NCHW, out_layout=NCHW)
+
+
+class VQVAE(nn.Module):
+    """models/vqvae.py:10-44."""
+
+    def __init__(self, h_dim, res_h_dim, n_res_layers, n_embeddings, embedding_dim, beta,
+                 save_img_embedding_map=False):
+        super().__init__()
+        self.encoder = Encoder(3, h_dim, n_res_layers, res_h_dim)
+        self.pre_quantization_conv = _PointwiseConv2d(h_dim, embedding_dim, kernel_size=1, stride=1)
+        self.vector_quantization = VectorQuantizer(n_embeddings, embedding_dim, beta)
+        self.decoder = Decoder(embedding_dim, h_dim, n_res_layers, res_h_dim)
+        if save_img_embedding_map:
+            self.img_to_embedding_map = {i: [] for i in range(n_embeddings)}
+        else:
+            self.img_to_embedding_map = None
+        # batch-sharded inference: set to a torch.distributed process group so that
+        # embedding_loss / perplexity equal the single-process values
+        self.process_group = None
+        self.last_min_encoding_indices = None
+
+    def _encode_rows(self, x):
+        x = _prep_input(x, 3, "VQVAE")
+        if x.shape[2] % 4 or x.shape[3] % 4:
+            raise RuntimeError("VQVAE: image height and width must be divisible by 4 (Q11)")
+        h, B, H, W = self.encoder._forward_nhwc(x)
+        z_e = _run_conv(self.pre_quantization_conv, h, B, H, W)              # NHWC (B,H,W,D)
+        return z_e, B, H, W
+
+    def forward(self, x, verbose=False):
+        z_e, B, H, W = self._encode_rows(x)                                  # vqvae.py:31-33
+        vq = self.vector_quantization
+        D = vq.e_dim
+        embedding_loss, zq, perplexity, idx = vq._quantize_rows(z_e.view(-1, D), self.process_group)
+        self.last_min_encoding_indices = idx.view(-1, 1)
+        x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
+        if verbose:                                                          # :38-42 (Q8)
+            print('original data shape:', x.shape)
+            print('encoded data shape:', torch.Size((B, D, H, W)))
+            print('recon data shape:', x_hat.shape)
+            assert False
+        return embedding_loss, x_hat, perplexity
+
+    # ---- the two halves callers use around the path ----------
+    def encode(self, x):
+        """images -> min_encoding_indices (N,1) int64 (README step 2 / notebook cell 1)."""
+        z_e, B, H, W = self._encode_rows(x)
+        _, _, _, idx = self.vector_quantization._quantize_rows(z_e.view(-1, self.vector_quantization.e_dim))
+        return idx.view(-1, 1)
+
+    def decode(self, indices, latent_hw):
+        """min_encoding_indices -> images (notebook cell 13 ``generate_samples``): the
+        one-hot matmul replaced by a codebook row gather."""
+        H, W = latent_hw
+        vq = self.vector_quantization
+        rows = ops.gather_rows(indices, vq._codebook())
+        B = rows.shape[0] // (H * W)
+        return self.decoder._forward_from_nhwc(rows.view(B, H, W, vq.e_dim), B, H, W)

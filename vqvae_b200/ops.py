@@ -1,0 +1,132 @@
+"""Torch-tensor front end of the C ABI: allocation and stream plumbing only.
+
+PyTorch owns every buffer and the current stream; all arithmetic happens inside
+libvqvae_b200.so.  There is NO CPU path: a non-CUDA tensor raises.
+"""
+import torch
+
+from . import _lib
+from ._lib import BF16, FP32, NCHW, NHWC, TF32, check, lib  # noqa: F401
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"vqvae_b200: {what} must be a CUDA tensor -- this implementation is sm_100a-only "
+            "and has no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def pack_conv_weight(w, transposed):
+    """(Cout,Cin,kh,kw) conv / (Cin,Cout,kh,kw) conv-transpose weight -> tap-major
+    fp32 GEMM operand [(r*kw+s)*Cin+ci][co] (vqb_pack_conv_weight_f32)."""
+    _require_cuda(w, "weight")
+    w = _f32c(w.detach())
+    if transposed:
+        cin, cout, kh, kw = w.shape
+    else:
+        cout, cin, kh, kw = w.shape
+    out = torch.empty((kh * kw * cin, cout), dtype=torch.float32, device=w.device)
+    check(lib().vqb_pack_conv_weight_f32(w.data_ptr(), out.data_ptr(), cout, cin, kh, kw,
+                                         int(bool(transposed)), _stream()), "pack_conv_weight")
+    return out
+
+
+def conv_out_hw(h, w, kh, kw, stride, pad, transposed):
+    if transposed:
+        return (h - 1) * stride - 2 * pad + kh, (w - 1) * stride - 2 * pad + kw
+    return (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+
+
+def conv2d(x, w_packed, bias, *, B, Cin, H, W, Cout, kh, kw, stride, pad, transposed=False,
+           in_layout=NHWC, out_layout=NHWC, relu=False, skip=None, precision=FP32):
+    """One nn.Conv2d / nn.ConvTranspose2d forward (+bias, +skip, +ReLU) on raw buffers.
+    `x` is any contiguous CUDA fp32 tensor holding the (B,Cin,H,W) activation in
+    `in_layout`; returns a new tensor in `out_layout` ((B,Cout,OH,OW) or (B,OH,OW,Cout))."""
+    _require_cuda(x, "input")
+    oh, ow = conv_out_hw(H, W, kh, kw, stride, pad, transposed)
+    if oh <= 0 or ow <= 0:
+        raise RuntimeError(f"conv output size is non-positive ({oh}x{ow})")
+    shape = (B, Cout, oh, ow) if out_layout == NCHW else (B, oh, ow, Cout)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    check(lib().vqb_conv2d_f32(
+        x.data_ptr(), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+        skip.data_ptr() if skip is not None else None, out.data_ptr(),
+        B, Cin, H, W, Cout, kh, kw, stride, pad, int(bool(transposed)), in_layout, out_layout,
+        int(bool(relu)), precision, _stream()), "conv2d")
+    return out
+
+
+def vq_forward(z_rows, codebook):
+    """Fused VectorQuantizer core on (N,D) rows -> (idx int64 (N,), zq (N,D), sse f64 (1,),
+    hist int32 (K,))."""
+    _require_cuda(z_rows, "z")
+    N, D = z_rows.shape
+    K = codebook.shape[0]
+    dev = z_rows.device
+    idx = torch.empty((N,), dtype=torch.int64, device=dev)
+    zq = torch.empty((N, D), dtype=torch.float32, device=dev)
+    sse = torch.empty((1,), dtype=torch.float64, device=dev)
+    hist = torch.empty((K,), dtype=torch.int32, device=dev)
+    ws_bytes = lib().vqb_vq_workspace_bytes(N, K, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    check(lib().vqb_vq_forward_f32(z_rows.data_ptr(), codebook.data_ptr(), N, K, D, idx.data_ptr(),
+                                   zq.data_ptr(), sse.data_ptr(), hist.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, _stream()), "vq_forward")
+    return idx, zq, sse, hist
+
+
+def vq_finish(sse, hist, N, K, D, beta):
+    """(loss, perplexity) fp32 0-dim CUDA tensors from the (all-reduced) sse / hist."""
+    out = torch.empty((2,), dtype=torch.float32, device=hist.device)
+    check(lib().vqb_vq_finish_f32(sse.data_ptr(), hist.data_ptr(), N, K, D, float(beta),
+                                  out.data_ptr(), out.data_ptr() + 4, _stream()), "vq_finish")
+    return out[0], out[1]
+
+
+def onehot(idx, K):
+    N = idx.numel()
+    out = torch.empty((N, K), dtype=torch.float32, device=idx.device)
+    check(lib().vqb_onehot_f32(idx.data_ptr(), N, K, out.data_ptr(), _stream()), "onehot")
+    return out
+
+
+def gather_rows(idx, codebook):
+    _require_cuda(idx, "indices")
+    idx = idx.reshape(-1).to(torch.int64).contiguous()
+    K, D = codebook.shape
+    out = torch.empty((idx.numel(), D), dtype=torch.float32, device=idx.device)
+    check(lib().vqb_gather_rows_f32(idx.data_ptr(), codebook.data_ptr(), idx.numel(), K, D,
+                                    out.data_ptr(), _stream()), "gather_rows")
+    return out
+
+
+def nchw_to_nhwc(x):
+    _require_cuda(x, "input")
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    check(lib().vqb_nchw_to_nhwc_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, _stream()), "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib().vqb_nhwc_to_nchw_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, _stream()), "nhwc_to_nchw")
+    return out
+
+
+def relu_(x):
+    """In-place ReLU on a contiguous fp32 CUDA tensor (residual.py:19 side effect)."""
+    check(lib().vqb_relu_f32(x.data_ptr(), x.numel(), _stream()), "relu_")
+    return x
