@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of VQVAE.forward (enc + VQ + dec) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg3] [--precision fp32|tf32|bf16]
+
+One "step" = one VQVAE.forward over one batch of synthetic images per GPU.
+Workload at N=1 = BASELINE.json configs[1] (cfg2: B=256, 3x32x32, K=512, D=64, fp32),
+per-GPU batch fixed as N grows (weak scaling, batch-sharded, one tiny all-reduce of the
+code histogram + SSE per forward).  Prints ONE JSON line (rank 0).
+
+  value      whole-job images/sec, inputs resident in HBM, device time (CUDA events per
+             step, L2 flushed between steps, max over ranks)
+  e2e        same metric through the public nn.Module call with HOST buffers: pinned
+             host -> device copy of x, forward, device -> host copy of x_hat + scalars,
+             all inside the timed region
+  roofline   dominant kernel of the step, timed live with CUDA events
+  cpu_baseline  the reference's CPU forward (oracle/torch_port.py, "port") on the host cores
+  --impl reference  times that CPU port on the same config and prints the same line shape
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (per-GPU batch, image size, K, D, flops per image [SURVEY 8d], description)
+    "cfg2": dict(batch=256, size=32, K=512, D=64, mflop_per_img=91.2,
+                 desc="VQVAE.forward bs=256 3x32x32 K=512 D=64 (BASELINE configs[1])"),
+    "cfg3": dict(batch=128, size=256, K=1024, D=64, mflop_per_img=6106.9,
+                 desc="VQVAE.forward bs=128 3x256x256 K=1024 D=64 (BASELINE configs[2])"),
+}
+HP = dict(h_dim=128, res_h_dim=32, n_res_layers=2)
+METRIC = "images/sec VQVAE fwd (enc+VQ+dec)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_forward_timer(wl, budget_s, min_iters=3, max_iters=50, warmup=2, threads=None):
+    """Time oracle/torch_port.vqvae_forward (the reference's forward restated on the
+    torch CPU ops it calls) on this host.  Returns (images/sec, iters, seconds, cores)."""
+    from oracle import torch_port
+    from oracle.weights import make_images, make_state_dict
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in
+          make_state_dict(seed=0, n_embeddings=wl["K"], embedding_dim=wl["D"], **HP).items()}
+    B = wl["batch"]
+    x = torch.from_numpy(make_images(B, wl["size"], seed=1))
+    for _ in range(warmup):
+        torch_port.vqvae_forward(x, sd, HP["n_res_layers"])
+    n, t0 = 0, time.perf_counter()
+    while True:
+        torch_port.vqvae_forward(x, sd, HP["n_res_layers"])
+        n += 1
+        el = time.perf_counter() - t0
+        if n >= max_iters or (n >= min_iters and el >= budget_s):
+            break
+    return B * n / el, n, el, cores
+
+
+def cpu_sample_batch(wl):
+    # bounded sample: the 256x256 workload costs seconds per image on a CPU
+    return dict(wl, batch=min(wl["batch"], 256 if wl["size"] <= 32 else 4))
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    swl = cpu_sample_batch(wl)
+    from oracle import torch_port
+    from oracle.weights import make_images, make_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in
+          make_state_dict(seed=0, n_embeddings=wl["K"], embedding_dim=wl["D"], **HP).items()}
+    x = torch.from_numpy(make_images(swl["batch"], swl["size"], seed=1))
+    for _ in range(args.warmup):
+        torch_port.vqvae_forward(x, sd, HP["n_res_layers"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        torch_port.vqvae_forward(x, sd, HP["n_res_layers"])
+    el = time.perf_counter() - t0
+    val = swl["batch"] * args.steps / el
+    sample = f"{args.steps} forwards of B={swl['batch']} 3x{swl['size']}x{swl['size']} (torch CPU ops, {cores} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": wl["desc"], "sample_batch": swl["batch"]},
+        "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import vqvae_b200
+    from vqvae_b200 import ops
+    from models.vqvae import VQVAE
+    from oracle.weights import make_images, make_state_dict  # synthetic weights/images only
+
+    vqvae_b200.set_precision(args.precision)
+    B, S, K, D = wl["batch"], wl["size"], wl["K"], wl["D"]
+    sd = make_state_dict(seed=0, n_embeddings=K, embedding_dim=D, **HP)
+    model = VQVAE(HP["h_dim"], HP["res_h_dim"], HP["n_res_layers"], K, D, 0.25)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model = model.to(dev).eval()
+    if world > 1:
+        model.process_group = dist.group.WORLD
+    # every rank gets its own shard of the global batch (different seed per rank)
+    x_host = torch.from_numpy(make_images(B, S, seed=1 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---- the step: eager once (also packs weights), then captured in a CUDA graph ----
+    l0 = ops.launch_count()
+    loss, x_hat, perp = model(x_dev)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+    use_graph = not args.no_graph
+    graph = None
+    static_x = x_dev.clone()
+    out = (loss, x_hat, perp)
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    model(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = model(static_x)
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover - reported in the JSON line
+            graph, use_graph = None, False
+            print(f"[bench] CUDA graph capture failed ({e}); running eagerly", file=sys.stderr)
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            return out
+        return model(static_x)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- device-resident timing: K steps, L2 flushed between, events per step ---------
+    clocks = ClockSampler(local_rank)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s0, s1 in evs:
+        flush.zero_()
+        s0.record()
+        step()
+        s1.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- end to end: host buffers, copies inside the timed region -----------------------
+    xh_host = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+    sc_host = torch.empty((2,), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        static_x.copy_(x_host, non_blocking=True); o = step()
+        xh_host.copy_(o[1], non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        static_x.copy_(x_host, non_blocking=True)
+        o = step()
+        xh_host.copy_(o[1], non_blocking=True)
+        sc_host[0:1].copy_(o[0].reshape(1), non_blocking=True)
+        sc_host[1:2].copy_(o[2].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller reads the result every step
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clock_info = clocks.stop()
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = t[0].item(), t[1].item()
+    imgs = B * world * args.steps
+    value = imgs / (dev_ms * 1e-3)
+    e2e_value = imgs / e2e_s
+
+    # ---- per-kernel breakdown with CUDA events (eager launches behind a spin kernel) ----
+    breakdown = {}
+    if rank == 0:
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            ops.PROFILE = []
+            torch.cuda._sleep(4_000_000)        # keep the stream busy while the host enqueues
+            model(static_x)
+            torch.cuda.synchronize()
+            for label, a, b in ops.PROFILE:
+                breakdown.setdefault(label, []).append(a.elapsed_time(b))
+            ops.PROFILE = None
+    peaks = load_peaks()
+    roofline = None
+    kernels = []
+    if breakdown:
+        per_label = {k: (float(np.mean(v)) / 1.0, len(v) // 5) for k, v in breakdown.items()}
+        # a label called c times per forward: mean is per call; total = mean * c
+        tot = {k: m * c for k, (m, c) in per_label.items()}
+        step_ms = sum(tot.values())
+        kernels = sorted(({"kernel": k, "calls": per_label[k][1], "ms_per_call": per_label[k][0],
+                           "share": tot[k] / step_ms} for k in tot), key=lambda r: -r["share"])
+        top = kernels[0]
+        roofline = kernel_roofline(top, B, S, K, D, peaks, args.precision)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.skip_cpu:
+        swl = cpu_sample_batch(wl)
+        v, n, el, cores = cpu_forward_timer(swl, args.cpu_seconds)
+        cpu = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
+               "sample": f"{n} forwards of B={swl['batch']} 3x{S}x{S} in {el:.1f}s "
+                         f"(oracle/torch_port.py = reference forward on torch CPU ops, {cores} threads)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"batch-shard x{world}", "l2": "flushed between timed steps (256 MiB memset)",
+                   "launch": "cuda-graph replay" if graph is not None else "eager",
+                   "weights": "synthetic seeded (oracle/weights.py), reference architecture h=128 res_h=32 n_res=2"},
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(xh_host.numel() * 4 + 8), "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clock_info,
+        "roofline": roofline,
+        "kernels": kernels[:8],
+        "cpu_baseline": cpu,
+        "peaks": peaks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(top, B, S, K, D, peaks, precision):
+    """Roofline of the dominant C-ABI call from its label (algorithmic work per launch,
+    DESIGN.md 'Kernels and rooflines')."""
+    label = top["kernel"]
+    ms = top["ms_per_call"]
+    if label.startswith("vq "):
+        N = B * (S // 4) ** 2
+        flops = 2.0 * N * K * D
+        byts = N * (2 * D * 4 + 8) + K * D * 4
+        t_hbm = byts / (peaks["hbm"] * 1e9)
+        tensor_peak = peaks["bf16"] * (0.5 if precision != "bf16" else 1.0)
+        t_tc = flops / (tensor_peak * 1e12)
+        if t_tc >= t_hbm:
+            ach = flops / (ms * 1e-3) / 1e12
+            return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"]}
+        ach = byts / (ms * 1e-3) / 1e9
+        return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
+    # conv label: "conv[T] Cin->Cout k{k}s{s} HxW[ +skip]"
+    parts = label.split()
+    transposed = parts[0] == "convT"
+    cin, cout = (int(v) for v in parts[1].split("->"))
+    k = int(parts[2][1:parts[2].index("s")])
+    s = int(parts[2][parts[2].index("s") + 1:])
+    h, w = (int(v) for v in parts[3].split("x"))
+    if transposed:
+        macs = B * h * w * cin * cout * k * k            # every input pixel touches k*k*Cout
+    else:
+        oh, ow = (h + 2 - k) // s + 1 if k > 1 else h, (w + 2 - k) // s + 1 if k > 1 else w
+        macs = B * oh * ow * cin * cout * k * k
+    flops = 2.0 * macs
+    tensor_peak = peaks["bf16"] * (1.0 if precision == "bf16" else 0.5)
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"],
+            "note": "tf32/fp32 layers are held against half the measured bf16 cuBLAS peak"}
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,10 @@ const char *vqb_error_string(int code);
 /* SM count and compute capability of the current device. */
 int vqb_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Number of kernels this process has launched through the library so far (bench.py
+ * reports it as gpu_launches).                                                     */
+unsigned long long vqb_launch_count(void);
+
 /* ---- weight packing (once per load_state_dict) --------------------------------
  * nn.Conv2d weight (Cout,Cin,kh,kw)          encoder.py:29-36, residual.py:20-24,
  *                                            vqvae.py:16-17

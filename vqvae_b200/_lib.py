@@ -33,6 +33,7 @@ SIGNATURES = {
     "vqb_nchw_to_nhwc_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vqb_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "vqb_relu_f32": (_i, [_vp, _i64, _vp]),
+    "vqb_launch_count": (C.c_ulonglong, []),
 }
 
 

@@ -5,6 +5,9 @@ size_t vq_exact_workspace_bytes(int K);
 int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq,
                     double *sse, int *hist, void *ws, cudaStream_t s);
 
+unsigned long long g_vqb_launches = 0;
+extern "C" unsigned long long vqb_launch_count(void) { return g_vqb_launches; }
+
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
 
 extern "C" const char *vqb_error_string(int code) {

@@ -30,4 +30,8 @@ struct ConvLaunch {
 int launch_conv_ffma(const ConvLaunch &p, cudaStream_t s);
 int launch_conv_small_cout(const ConvLaunch &p, cudaStream_t s);
 
+// process-wide count of kernels launched through the C ABI (vqb_launch_count)
+extern unsigned long long g_vqb_launches;
+#define VQB_COUNT_LAUNCH(n) (g_vqb_launches += (n))
+
 static inline int vqb_cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

@@ -293,6 +293,7 @@ int launch_conv_ffma(const ConvLaunch &p, cudaStream_t s) {
         if (vec_a) conv_ffma_kernel<128, 32, 4, 4, true><<<grid, NT, 0, s>>>(p);
         else conv_ffma_kernel<128, 32, 4, 4, false><<<grid, NT, 0, s>>>(p);
     }
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -302,5 +303,6 @@ int launch_conv_small_cout(const ConvLaunch &p, cudaStream_t s) {
     const size_t smem = (size_t)p.ntaps * p.Cin * 4 * sizeof(float);
     if (smem > 48 * 1024) return VQB_ERR_UNSUPPORTED;
     conv_small_cout_kernel<<<(unsigned)((M + 255) / 256), 256, smem, s>>>(p);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

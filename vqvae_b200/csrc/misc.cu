@@ -119,6 +119,7 @@ extern "C" int vqb_pack_conv_weight_f32(const float *w, float *packed, int Cout,
     const long long total = (long long)Cout * Cin * kh * kw;
     pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, packed, Cout, Cin, kh, kw,
                                                                               transposed);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -127,6 +128,7 @@ static int transpose_launch(const float *in, float *out, int Bt, int R, int Cc, 
     dim3 grid((Cc + 31) / 32, (R + 31) / 32, Bt), block(32, 8);
     if (grid.y > 65535) return VQB_ERR_UNSUPPORTED;
     transpose_kernel<<<grid, block, 0, s>>>(in, out, R, Cc);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -144,6 +146,7 @@ extern "C" int vqb_vq_finish_f32(const double *sse, const int32_t *hist, int64_t
                                  float *loss, float *perplexity, void *stream) {
     if (!sse || !hist || !loss || !perplexity || N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
     vq_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sse, hist, N, K, D, beta, loss, perplexity);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -154,6 +157,7 @@ extern "C" int vqb_onehot_f32(const int64_t *idx, int64_t N, int K, float *oneho
         onehot_kernel<<<grid_for(N * (long long)(K / 4), 256), 256, 0, (cudaStream_t)stream>>>(ip, N, K, onehot);
     else
         onehot_scalar_kernel<<<grid_for(N * (long long)K, 256), 256, 0, (cudaStream_t)stream>>>(ip, N, K, onehot);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -162,6 +166,7 @@ extern "C" int vqb_gather_rows_f32(const int64_t *idx, const float *codebook, in
     if (!idx || !codebook || !rows || N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
     gather_rows_kernel<<<grid_for(N * (long long)D, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const long long *>(idx), codebook, N, K, D, rows);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
 
@@ -169,5 +174,6 @@ extern "C" int vqb_relu_f32(float *x, int64_t n, void *stream) {
     if (!x || n < 0) return VQB_ERR_BAD_ARG;
     if (n == 0) return 0;
     relu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n);
+    VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -219,10 +219,11 @@ int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, l
                         VR * sizeof(int);
     const int use_smem_hist = (base + (size_t)K * sizeof(int) <= 200 * 1024) ? 1 : 0;
     const size_t smem = base + (use_smem_hist ? (size_t)K * sizeof(int) : 0);
-    if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
+    constexpr size_t kMaxDyn = 227 * 1024 - 1024;   // 227 KB per CTA minus static smem
+    if (smem > kMaxDyn) return VQB_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(vq_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(vq_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -239,5 +240,6 @@ int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, l
     if (grid < 1) grid = 1;
     vq_exact_kernel<<<(unsigned)grid, VNT, smem, s>>>(z, E, bn, N, K, D, idx, zq, partials, hist, use_smem_hist);
     sum_partials_kernel<<<1, 256, 0, s>>>(partials, (int)grid, sse);
+    VQB_COUNT_LAUNCH(3);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -20,6 +20,33 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-call CUDA-event timing (bench.py's kernel breakdown): when PROFILE is a
+# list, every C-ABI compute call appends (label, start_event, end_event).
+PROFILE = None
+
+
+class _Span:
+    __slots__ = ("label", "start", "end")
+
+    def __init__(self, label):
+        self.label = label
+        self.start = self.end = None
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def done(self):
+        if self.start is not None:
+            self.end.record()
+            PROFILE.append((self.label, self.start, self.end))
+
+
+def launch_count() -> int:
+    """Kernels launched so far through the C ABI by this process."""
+    return int(lib().vqb_launch_count())
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
@@ -58,11 +85,14 @@ def conv2d(x, w_packed, bias, *, B, Cin, H, W, Cout, kh, kw, stride, pad, transp
         raise RuntimeError(f"conv output size is non-positive ({oh}x{ow})")
     shape = (B, Cout, oh, ow) if out_layout == NCHW else (B, oh, ow, Cout)
     out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    span = _Span(f"conv{'T' if transposed else ''} {Cin}->{Cout} k{kh}s{stride} {H}x{W}"
+                 f"{' +skip' if skip is not None else ''}")
     check(lib().vqb_conv2d_f32(
         x.data_ptr(), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
         skip.data_ptr() if skip is not None else None, out.data_ptr(),
         B, Cin, H, W, Cout, kh, kw, stride, pad, int(bool(transposed)), in_layout, out_layout,
         int(bool(relu)), precision, _stream()), "conv2d")
+    span.done()
     return out
 
 
@@ -79,9 +109,11 @@ def vq_forward(z_rows, codebook):
     hist = torch.empty((K,), dtype=torch.int32, device=dev)
     ws_bytes = lib().vqb_vq_workspace_bytes(N, K, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    span = _Span(f"vq N={N} K={K} D={D}")
     check(lib().vqb_vq_forward_f32(z_rows.data_ptr(), codebook.data_ptr(), N, K, D, idx.data_ptr(),
                                    zq.data_ptr(), sse.data_ptr(), hist.data_ptr(), ws.data_ptr(),
                                    ws_bytes, _stream()), "vq_forward")
+    span.done()
     return idx, zq, sse, hist
 
 
