@@ -98,6 +98,18 @@ int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, 
                        int64_t *idx, float *zq, double *sse, int32_t *hist,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Kernel choice of vqb_vq_forward_f32: 0 = auto (tcgen05 kernel when D == 64, else the
+ * exact FFMA kernel), 1 = always the FFMA kernel, 2 = require the tcgen05 kernel.  Both
+ * produce bit-identical idx / zq; the switch exists for tests and benchmarks.        */
+int vqb_set_vq_kernel(int which);
+
+/* Diagnostic twin of vqb_vq_forward_f32 (tcgen05 kernel only): additionally dumps the
+ * approximate TF32 scores s = ||e||^2 - 2 z.e as (N, ceil(K/256)*256) floats.        */
+int vqb_debug_vq_scores_f32(const float *z, const float *codebook, int64_t N, int K, int D,
+                            int64_t *idx, float *zq, double *sse, int32_t *hist,
+                            void *workspace, size_t workspace_bytes, float *scores,
+                            void *stream);
+
 /* loss = (1+beta)*sse/(N*D) and perplexity = exp(-sum p log(p+1e-10)), p = hist/N,
  * written as two fp32 device scalars (quantizer.py:63-64, :70-71).  Separate from
  * the VQ kernel so a batch-sharded caller can all-reduce (hist, sse) in between.  */

@@ -5,7 +5,18 @@ size_t vq_exact_workspace_bytes(int K);
 int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq,
                     double *sse, int *hist, void *ws, cudaStream_t s);
 
+size_t vq_tc_workspace_bytes(int K);
+bool vq_tc_supported(long long N, int K, int D);
+int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
+                 int *hist, void *ws, float *dbg, cudaStream_t s);
+
 unsigned long long g_vqb_launches = 0;
+static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel
+extern "C" int vqb_set_vq_kernel(int which) {
+    if (which < 0 || which > 2) return VQB_ERR_BAD_ARG;
+    g_vq_kernel = which;
+    return 0;
+}
 extern "C" unsigned long long vqb_launch_count(void) { return g_vqb_launches; }
 
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
@@ -118,7 +129,8 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
 extern "C" size_t vqb_vq_workspace_bytes(int64_t N, int K, int D) {
     (void)N; (void)D;
     if (K <= 0) return 0;
-    return vq_exact_workspace_bytes(K);
+    const size_t a = vq_exact_workspace_bytes(K), b = vq_tc_workspace_bytes(K);
+    return a > b ? a : b;
 }
 
 extern "C" int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
@@ -131,6 +143,21 @@ extern "C" int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t
     const uintptr_t al = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(codebook) |
                          reinterpret_cast<uintptr_t>(zq) | reinterpret_cast<uintptr_t>(workspace);
     if (al & 15) return VQB_ERR_ALIGNMENT;
+    const bool tc_ok = vq_tc_supported(N, K, D);
+    if (g_vq_kernel == 2 && !tc_ok) return VQB_ERR_UNSUPPORTED;
+    if (tc_ok && g_vq_kernel != 1)
+        return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
+                            nullptr, (cudaStream_t)stream);
     return launch_vq_exact(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
                            (cudaStream_t)stream);
+}
+
+extern "C" int vqb_debug_vq_scores_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
+                                       float *zq, double *sse, int32_t *hist, void *workspace,
+                                       size_t workspace_bytes, float *scores, void *stream) {
+    if (!z || !codebook || !idx || !zq || !sse || !hist || !workspace || !scores) return VQB_ERR_BAD_ARG;
+    if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
+    if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
+    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores,
+                        (cudaStream_t)stream);
 }

@@ -1,0 +1,479 @@
+// vq_tc.cu -- fused VectorQuantizer.forward on tcgen05 tensor cores (sm_100a), D = 64.
+//
+// Replaces quantizer.py:45-71.  One persistent, warp-specialised CTA per SM:
+//   warp 0      TMA producer: z row tiles (128 x 64 fp32) and codebook chunks
+//               (256 x 64 fp32) land in shared memory in the 128-byte-swizzled K-major
+//               layout UMMA consumes; ||e_k||^2 of the chunk comes with a 1-D bulk copy.
+//               A codebook of <= 512 codes stays resident in shared memory.
+//   warp 1      issues tcgen05.mma kind::tf32 (M=128, N=256, K=8 x 8): the dense
+//               contraction z . e^T, fp32 accumulators in TMEM, double buffered
+//               (2 x 256 columns) so the epilogue of chunk c overlaps the MMA of c+1.
+//   warp 2      allocates / frees TMEM.
+//   warps 4-11  epilogue: thread = (row, column half).  tcgen05.ld the scores, form
+//               s = ||e||^2 - 2 z.e, keep per-8-code group minima, and push every group
+//               within tau of the running minimum into a small per-thread list.
+//
+// Bit-exactness (DESIGN.md "VQ arithmetic contract"): the TF32 scores only SELECT
+// candidates.  tau bounds twice the worst-case error of a score (tf32 truncation of
+// both operands, fp32 accumulation, and the rounding of the canonical formula), so the
+// canonical fp32 winner -- and every code tied with it -- is always inside a listed
+// group.  Listed groups are re-scored with the canonical arithmetic of
+// oracle/csrc/oracle.c (sequential fmaf chain, fl(fl(A+B) - fl(2M)), first minimum
+// wins, NaN wins), so idx and z_q are bit-identical to vq_exact.cu and to the oracle.
+// Rows with non-finite data, a non-finite codebook, or an overflowing candidate list
+// fall back to scanning every code exactly.
+//
+// The same launch gathers e_idx, writes z_q = z + (e - z), accumulates the SSE (double)
+// and a shared-memory code histogram.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int TM = 128;          // latent rows per tile (UMMA M)
+constexpr int CN = 256;          // codes per chunk (UMMA N)
+constexpr int DD = 64;           // embedding dim handled by this kernel
+constexpr int NTHREADS = 384;    // 12 warps
+constexpr int LCAP = 12;         // candidate-group list capacity per thread
+constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
+constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
+constexpr int HIST_MAX = 1024;
+
+constexpr int OFF_Z = 0;
+constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
+constexpr int OFF_B = OFF_E + 2 * ESTAGE;
+constexpr int OFF_LIST = OFF_B + 2 * CN * 4;
+constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;
+constexpr int OFF_XBD = OFF_XMIN + 256 * 4;
+constexpr int OFF_XBK = OFF_XBD + 256 * 4;
+constexpr int OFF_HIST = OFF_XBK + 256 * 4;
+constexpr int OFF_BAR = OFF_HIST + HIST_MAX * 4;
+constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
+constexpr int OFF_RED = OFF_TMEM + 64;
+constexpr int SMEM_TOTAL = OFF_RED + 64;
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;   // slack for the manual 1024-byte alignment
+static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
+
+enum { Z_FULL = 0, Z_EMPTY = 2, E_FULL = 4, E_EMPTY = 6, T_FULL = 8, T_EMPTY = 10 };
+
+struct VqTcParams {
+    const float *E;        // (K, 64) codebook
+    const float *bn;       // (nchunks*256) canonical ||e_k||^2, +inf past K
+    const float *scal;     // [0] = upper bound of max ||e_k||, [1] = non-finite flag (int)
+    long long N;
+    int K, nchunks;
+    long long *idx;
+    float *zq;
+    double *partials;
+    int *hist;
+    float *dbg;            // optional (N, nchunks*256) raw approximate scores
+};
+
+__device__ __forceinline__ bool vq_better(float dn, int kn, float db, int kb) {
+    const bool nn = dn != dn, nb = db != db;            // torch.argmin: NaN is the minimum
+    if (nn || nb) return nn && (!nb || kn < kb);
+    return dn < db || (dn == db && kn < kb);
+}
+
+// workspace prep: canonical code norms (quantizer.py:50), their maximum, a non-finite flag
+__global__ void vq_tc_prep_kernel(const float *__restrict__ E, int K, int Kpad, float *__restrict__ bn,
+                                  unsigned *__restrict__ scal) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    if (k >= K) { bn[k] = __int_as_float(0x7f800000); return; }
+    const float *e = E + (size_t)k * DD;
+    float s = 0.f;
+    for (int d = 0; d < DD; ++d) s = __fadd_rn(s, __fmul_rn(e[d], e[d]));
+    bn[k] = s;
+    if (!(s < __int_as_float(0x7f800000))) atomicOr(&scal[1], 1u);       // inf or NaN
+    else atomicMax(&scal[0], __float_as_uint(sqrtf(s) * 1.00001f));       // positive floats order as uints
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme, const VqTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = sbase + OFF_BAR;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    float *bsm = reinterpret_cast<float *>(sm + OFF_B);
+    int *hist_s = reinterpret_cast<int *>(sm + OFF_HIST);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
+
+    const long long ntiles = (p.N + TM - 1) / TM;
+    const int nchunks = p.nchunks;
+    const bool resident = nchunks <= 2;
+    const bool smem_hist = p.K <= HIST_MAX;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tmz);
+        ptx::prefetch_tmap(&tme);
+        ptx::mbar_init(bar(Z_FULL + 0), 1); ptx::mbar_init(bar(Z_FULL + 1), 1);
+        ptx::mbar_init(bar(Z_EMPTY + 0), 9); ptx::mbar_init(bar(Z_EMPTY + 1), 9);   // MMA commit + 8 epilogue warps
+        ptx::mbar_init(bar(E_FULL + 0), 1); ptx::mbar_init(bar(E_FULL + 1), 1);
+        ptx::mbar_init(bar(E_EMPTY + 0), 9); ptx::mbar_init(bar(E_EMPTY + 1), 9);
+        ptx::mbar_init(bar(T_FULL + 0), 1); ptx::mbar_init(bar(T_FULL + 1), 1);
+        ptx::mbar_init(bar(T_EMPTY + 0), 8); ptx::mbar_init(bar(T_EMPTY + 1), 8);
+        ptx::fence_mbar_init();
+    }
+    if (smem_hist)
+        for (int k = tid; k < p.K; k += NTHREADS) hist_s[k] = 0;
+    if (warp == 2) ptx::tmem_alloc(sbase + OFF_TMEM, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            long long gc = 0;
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int zs = it & 1;
+                ptx::mbar_wait(bar(Z_EMPTY + zs), ((it >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(bar(Z_FULL + zs), ZSTAGE);
+                const uint32_t zdst = sbase + OFF_Z + zs * ZSTAGE;
+                ptx::tma_load_2d(zdst, &tmz, bar(Z_FULL + zs), 0, (int)(tile * TM));
+                ptx::tma_load_2d(zdst + ZATOM, &tmz, bar(Z_FULL + zs), 32, (int)(tile * TM));
+                if (resident && it > 0) continue;
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int es = resident ? c : (int)(gc & 1);
+                    const uint32_t par = resident ? 0u : (uint32_t)((gc >> 1) & 1);
+                    ptx::mbar_wait(bar(E_EMPTY + es), par ^ 1);
+                    ptx::mbar_expect_tx(bar(E_FULL + es), ESTAGE + CN * 4);
+                    const uint32_t edst = sbase + OFF_E + es * ESTAGE;
+                    ptx::tma_load_2d(edst, &tme, bar(E_FULL + es), 0, c * CN);
+                    ptx::tma_load_2d(edst + EATOM, &tme, bar(E_FULL + es), 32, c * CN);
+                    ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, TM, CN);
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int zs = it & 1;
+                ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+                for (int c = 0; c < nchunks; ++c) {
+                    const long long gc = (long long)it * nchunks + c;
+                    int es;
+                    if (resident) {
+                        es = c;
+                        if (it == 0) ptx::mbar_wait(bar(E_FULL + es), 0);
+                    } else {
+                        es = (int)(gc & 1);
+                        ptx::mbar_wait(bar(E_FULL + es), (uint32_t)((gc >> 1) & 1));
+                    }
+                    const int ab = (int)(gc & 1);
+                    ptx::mbar_wait(bar(T_EMPTY + ab), (uint32_t)(((gc >> 1) & 1) ^ 1));
+                    ptx::tc_fence_after();
+                    const uint32_t za = sbase + OFF_Z + zs * ZSTAGE, ea = sbase + OFF_E + es * ESTAGE;
+#pragma unroll
+                    for (int ks = 0; ks < DD / 8; ++ks) {
+                        const uint64_t ad = ptx::smem_desc_sw128(za + (ks >> 2) * ZATOM + (ks & 3) * 32);
+                        const uint64_t bd = ptx::smem_desc_sw128(ea + (ks >> 2) * EATOM + (ks & 3) * 32);
+                        ptx::mma_tf32(tmem_base + ab * CN, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    ptx::tc_commit(bar(T_FULL + ab));
+                    if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
+                }
+                ptx::tc_commit(bar(Z_EMPTY + zs));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int et = tid - 128;               // 0..255
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int h = (warp - 4) >> 2;          // column half of every chunk
+        const int row = q * 32 + lane;          // accumulator row = TMEM lane
+        const float INF = __int_as_float(0x7f800000);
+        const float Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
+        const bool bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
+        float2 *lists = reinterpret_cast<float2 *>(sm + OFF_LIST);
+        float *xmin = reinterpret_cast<float *>(sm + OFF_XMIN);
+        float *xbd = reinterpret_cast<float *>(sm + OFF_XBD);
+        int *xbk = reinterpret_cast<int *>(sm + OFF_XBK);
+        const int Kpad = nchunks * CN;
+        double sse = 0.0;
+
+        // exact canonical distance of code k for this thread's row (zr in registers)
+        auto code_ptr_smem = [&](int k) -> const unsigned char * {
+            return sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128;
+        };
+
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int zs = it & 1;
+            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            float zr[DD];
+            {
+                const unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ (row & 7)) << 4));
+                        zr[a * 32 + c16 * 4 + 0] = v.x; zr[a * 32 + c16 * 4 + 1] = v.y;
+                        zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(Z_EMPTY + zs));
+
+            float A = 0.f;                                    // quantizer.py:49, canonical order
+#pragma unroll
+            for (int d = 0; d < DD; ++d) A = __fadd_rn(A, __fmul_rn(zr[d], zr[d]));
+            // S >= sum_d |z_d e_kd| for every k (Cauchy-Schwarz, rounded up)
+            const float S = sqrtf(A) * 1.00001f * Emax;
+            // 2 x (tf32 truncation of both operands on 2M: 2*2^-9*S, + fp32 accumulation and
+            // the canonical formula's own rounding), with margin.
+            const float tau = S * (0.0078125f + 0.0009765625f) + (A + Emax * Emax + S) * 1.9073486e-6f;
+            const bool slow_row = bad_codebook || !(A < INF) || !(tau < INF);
+
+            float run_min = INF, thr = INF;
+            int cnt = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const long long gc = (long long)it * nchunks + c;
+                const int ab = (int)(gc & 1);
+                const int es = resident ? c : (int)(gc & 1);
+                ptx::mbar_wait(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1));
+                ptx::tc_fence_after();
+                const float *bch = bsm + es * CN;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int col0 = h * 128 + j * 32;
+                    float v[32];
+                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * CN + col0), v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(bch + col0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(bch + col0 + g * 8 + 4);
+                        const float s0 = fmaf(v[g * 8 + 0], -2.f, b0.x), s1 = fmaf(v[g * 8 + 1], -2.f, b0.y);
+                        const float s2 = fmaf(v[g * 8 + 2], -2.f, b0.z), s3 = fmaf(v[g * 8 + 3], -2.f, b0.w);
+                        const float s4 = fmaf(v[g * 8 + 4], -2.f, b1.x), s5 = fmaf(v[g * 8 + 5], -2.f, b1.y);
+                        const float s6 = fmaf(v[g * 8 + 6], -2.f, b1.z), s7 = fmaf(v[g * 8 + 7], -2.f, b1.w);
+                        if (p.dbg) {
+                            const long long grow = tile * TM + row;
+                            if (grow < p.N) {
+                                float *dst = p.dbg + (size_t)grow * Kpad + c * CN + col0 + g * 8;
+                                dst[0] = s0; dst[1] = s1; dst[2] = s2; dst[3] = s3;
+                                dst[4] = s4; dst[5] = s5; dst[6] = s6; dst[7] = s7;
+                            }
+                        }
+                        const float gm = ptx::fmin3(ptx::fmin3(s0, s1, s2), ptx::fmin3(s3, s4, s5), fminf(s6, s7));
+                        if (gm <= thr) {
+                            if (cnt < LCAP) lists[cnt * 256 + et] = make_float2(gm, __int_as_float((c * CN + col0) / 8 + g));
+                            ++cnt;
+                        }
+                        run_min = fminf(run_min, gm);
+                        thr = run_min + tau;
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(bar(T_EMPTY + ab));
+                    if (!resident) ptx::mbar_arrive(bar(E_EMPTY + es));
+                }
+            }
+
+            // ---- approximate minimum of the whole row (both column halves) ----
+            xmin[et] = run_min;
+            ptx::named_bar_sync(1 + q, 64);
+            thr = fminf(run_min, xmin[et ^ 128]) + tau;
+
+            // ---- exact canonical re-scoring of the candidate groups ----
+            float bd = 0.f;
+            int bk = -1;
+            auto rescore = [&](int k) {
+                float M = 0.f, bnk;
+                if (resident) {
+                    const unsigned char *er = code_ptr_smem(k);
+                    const int sw = k & 7;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 e4 = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ sw) << 4));
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 0], e4.x, M);
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 1], e4.y, M);
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 2], e4.z, M);
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 3], e4.w, M);
+                        }
+                    bnk = bsm[k];
+                } else {
+                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);
+#pragma unroll
+                    for (int c16 = 0; c16 < 16; ++c16) {
+                        const float4 e4 = __ldg(er + c16);
+                        M = __fmaf_rn(zr[c16 * 4 + 0], e4.x, M);
+                        M = __fmaf_rn(zr[c16 * 4 + 1], e4.y, M);
+                        M = __fmaf_rn(zr[c16 * 4 + 2], e4.z, M);
+                        M = __fmaf_rn(zr[c16 * 4 + 3], e4.w, M);
+                    }
+                    bnk = __ldg(p.bn + k);
+                }
+                const float dist = __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));   // quantizer.py:49-51
+                if (bk < 0 || vq_better(dist, k, bd, bk)) { bd = dist; bk = k; }
+            };
+            if (!slow_row && cnt <= LCAP) {
+                for (int s = 0; s < cnt; ++s) {
+                    const float2 ent = lists[s * 256 + et];
+                    if (ent.x <= thr) {
+                        const int k0 = __float_as_int(ent.y) * 8;
+#pragma unroll 1
+                        for (int j = 0; j < 8; ++j)
+                            if (k0 + j < p.K) rescore(k0 + j);
+                    }
+                }
+            } else {
+                // non-finite data or list overflow (e.g. many duplicated codes): scan every code
+                for (int c = 0; c < nchunks; ++c)
+                    for (int kk = 0; kk < 128; ++kk) {
+                        const int k = c * CN + h * 128 + kk;
+                        if (k < p.K) rescore(k);
+                    }
+            }
+            xbd[et] = bd;
+            xbk[et] = bk;
+            ptx::named_bar_sync(1 + q, 64);
+            {
+                const float od = xbd[et ^ 128];
+                const int ok = xbk[et ^ 128];
+                if (ok >= 0 && (bk < 0 || vq_better(od, ok, bd, bk))) { bd = od; bk = ok; }
+            }
+
+            // ---- gather e_idx, straight-through z_q, SSE, histogram (this thread: 32 of 64 dims) ----
+            const long long grow = tile * TM + row;
+            if (grow < p.N) {
+                float *qdst = p.zq + (size_t)grow * DD + h * 32;
+                auto emit = [&](const float *zh) {
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        float4 e4;
+                        if (resident)
+                            e4 = *reinterpret_cast<const float4 *>(code_ptr_smem(bk) + h * EATOM + ((c16 ^ (bk & 7)) << 4));
+                        else
+                            e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)bk * DD + h * 32) + c16);
+                        float4 df, o;
+                        df.x = __fsub_rn(e4.x, zh[c16 * 4 + 0]); df.y = __fsub_rn(e4.y, zh[c16 * 4 + 1]);
+                        df.z = __fsub_rn(e4.z, zh[c16 * 4 + 2]); df.w = __fsub_rn(e4.w, zh[c16 * 4 + 3]);
+                        o.x = __fadd_rn(zh[c16 * 4 + 0], df.x); o.y = __fadd_rn(zh[c16 * 4 + 1], df.y);   // quantizer.py:67
+                        o.z = __fadd_rn(zh[c16 * 4 + 2], df.z); o.w = __fadd_rn(zh[c16 * 4 + 3], df.w);
+                        *reinterpret_cast<float4 *>(qdst + c16 * 4) = o;
+                        sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
+                    }
+                };
+                if (h == 0) {
+                    emit(zr);
+                    p.idx[grow] = bk;
+                    if (smem_hist) atomicAdd(&hist_s[bk], 1);
+                    else atomicAdd(&p.hist[bk], 1);
+                } else {
+                    emit(zr + 32);
+                }
+            }
+        }
+
+        // ---- CTA reduction of the SSE partial, histogram flush ----
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
+        double *red = reinterpret_cast<double *>(sm + OFF_RED);
+        if (lane == 0) red[warp - 4] = sse;
+        ptx::named_bar_sync(5, 256);
+        if (et == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            p.partials[blockIdx.x] = s;
+        }
+        if (smem_hist)
+            for (int k = et; k < p.K; k += 256) {
+                const int cval = hist_s[k];
+                if (cval) atomicAdd(&p.hist[k], cval);
+            }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void vq_tc_sum_partials(const double *__restrict__ partials, int n, double *__restrict__ out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off >= 1; off >>= 1) {
+        if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+// workspace: [bn: Kpad floats][scal: 256 B][partials: 256 doubles]
+size_t vq_tc_workspace_bytes(int K) {
+    const size_t Kpad = (size_t)((K + CN - 1) / CN) * CN;
+    return align256(Kpad * 4) + 256 + 256 * sizeof(double);
+}
+
+bool vq_tc_supported(long long N, int K, int D) {
+    return D == DD && N >= 1 && N < (1LL << 31) && K >= 1 && K <= (1 << 20);
+}
+
+int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
+                 int *hist, void *ws, float *dbg, cudaStream_t s) {
+    if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
+    const int nchunks = (K + CN - 1) / CN;
+    const int Kpad = nchunks * CN;
+    unsigned char *w = reinterpret_cast<unsigned char *>(ws);
+    float *bn = reinterpret_cast<float *>(w);
+    unsigned *scal = reinterpret_cast<unsigned *>(w + align256((size_t)Kpad * 4));
+    double *partials = reinterpret_cast<double *>(w + align256((size_t)Kpad * 4) + 256);
+
+    CUtensorMap tmz, tme;
+    int rc = vqb_encode_tmap_2d(&tmz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, z, DD, (uint64_t)N, DD * 4, 32, TM,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tme, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, E, DD, (uint64_t)K, DD * 4, 32, CN,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+
+    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)K, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(scal, 0, 256, s);
+    if (e != cudaSuccess) return (int)e;
+    vq_tc_prep_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(E, K, Kpad, bn, scal);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (N + TM - 1) / TM;
+    int grid = (int)(ntiles < sms ? ntiles : sms);
+    if (grid > 256) grid = 256;
+    VqTcParams p;
+    p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
+    p.N = N; p.K = K; p.nchunks = nchunks;
+    p.idx = idx; p.zq = zq; p.partials = partials; p.hist = hist; p.dbg = dbg;
+    vq_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, p);
+    vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
+    VQB_COUNT_LAUNCH(3);
+    return vqb_cuda_status(cudaGetLastError());
+}
