@@ -131,6 +131,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but carrying the 32 destination registers of the load as in/out operands so
+// that no consumer of v[] can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait32(float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                   "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                   "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;

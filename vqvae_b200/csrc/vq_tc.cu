@@ -4,14 +4,16 @@
 //   warp 0      TMA producer: z row tiles (128 x 64 fp32) and codebook chunks
 //               (256 x 64 fp32) land in shared memory in the 128-byte-swizzled K-major
 //               layout UMMA consumes; ||e_k||^2 of the chunk comes with a 1-D bulk copy.
-//               A codebook of <= 512 codes stays resident in shared memory.
+//               A codebook of <= 512 codes stays resident in shared memory.  The same
+//               thread TMA-stores finished z_q tiles (written in place over the z tile).
 //   warp 1      issues tcgen05.mma kind::tf32 (M=128, N=256, K=8 x 8): the dense
 //               contraction z . e^T, fp32 accumulators in TMEM, double buffered
 //               (2 x 256 columns) so the epilogue of chunk c overlaps the MMA of c+1.
 //   warp 2      allocates / frees TMEM.
-//   warps 4-11  epilogue: thread = (row, column half).  tcgen05.ld the scores, form
-//               s = ||e||^2 - 2 z.e, keep per-8-code group minima, and push every group
-//               within tau of the running minimum into a small per-thread list.
+//   warps 4-11  epilogue: thread = (row, column half).  tcgen05.ld the scores (double
+//               buffered in registers), form s = ||e||^2 - 2 z.e, keep per-8-code group
+//               minima, and push every group within tau of the running minimum into a
+//               small per-thread list.
 //
 // Bit-exactness (DESIGN.md "VQ arithmetic contract"): the TF32 scores only SELECT
 // candidates.  tau bounds twice the worst-case error of a score (tf32 truncation of
@@ -20,11 +22,14 @@
 // group.  Listed groups are re-scored with the canonical arithmetic of
 // oracle/csrc/oracle.c (sequential fmaf chain, fl(fl(A+B) - fl(2M)), first minimum
 // wins, NaN wins), so idx and z_q are bit-identical to vq_exact.cu and to the oracle.
-// Rows with non-finite data, a non-finite codebook, or an overflowing candidate list
-// fall back to scanning every code exactly.
+// The two threads of a row split each candidate group (4 codes each, 4 independent
+// chains).  Rows with non-finite data, a non-finite codebook, or overflowing candidate
+// lists fall back to scanning every code exactly.
 //
-// The same launch gathers e_idx, writes z_q = z + (e - z), accumulates the SSE (double)
+// The same launch gathers e_idx, forms z_q = z + (e - z), accumulates the SSE (double)
 // and a shared-memory code histogram.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -34,7 +39,8 @@ constexpr int TM = 128;          // latent rows per tile (UMMA M)
 constexpr int CN = 256;          // codes per chunk (UMMA N)
 constexpr int DD = 64;           // embedding dim handled by this kernel
 constexpr int NTHREADS = 384;    // 12 warps
-constexpr int LCAP = 12;         // candidate-group list capacity per thread
+constexpr int LCAP = 12;         // group list capacity per thread (pass 1)
+constexpr int CMAX = 4;          // candidate groups per thread after filtering
 constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
 constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
 constexpr int HIST_MAX = 1024;
@@ -43,9 +49,9 @@ constexpr int OFF_Z = 0;
 constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;
 constexpr int OFF_LIST = OFF_B + 2 * CN * 4;
-constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;
-constexpr int OFF_XBD = OFF_XMIN + 256 * 4;
-constexpr int OFF_XBK = OFF_XBD + 256 * 4;
+constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;      // float[256]; reused as int nc[256]
+constexpr int OFF_XBD = OFF_XMIN + 256 * 4;              // float[256]
+constexpr int OFF_XBK = OFF_XBD + 256 * 4;               // int[256]
 constexpr int OFF_HIST = OFF_XBK + 256 * 4;
 constexpr int OFF_BAR = OFF_HIST + HIST_MAX * 4;
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
@@ -54,7 +60,7 @@ constexpr int SMEM_TOTAL = OFF_RED + 64;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;   // slack for the manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
 
-enum { Z_FULL = 0, Z_EMPTY = 2, E_FULL = 4, E_EMPTY = 6, T_FULL = 8, T_EMPTY = 10 };
+enum { Z_FULL = 0, Q_FULL = 2, E_FULL = 4, E_EMPTY = 6, T_FULL = 8, T_EMPTY = 10 };
 
 struct VqTcParams {
     const float *E;        // (K, 64) codebook
@@ -63,10 +69,10 @@ struct VqTcParams {
     long long N;
     int K, nchunks;
     long long *idx;
-    float *zq;
     double *partials;
     int *hist;
     float *dbg;            // optional (N, nchunks*256) raw approximate scores
+    int flags;             // perf-experiment knobs (env VQB_TC_FLAGS), 0 in production
 };
 
 __device__ __forceinline__ bool vq_better(float dn, int kn, float db, int kb) {
@@ -74,6 +80,14 @@ __device__ __forceinline__ bool vq_better(float dn, int kn, float db, int kb) {
     if (nn || nb) return nn && (!nb || kn < kb);
     return dn < db || (dn == db && kn < kb);
 }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                     "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // workspace prep: canonical code norms (quantizer.py:50), their maximum, a non-finite flag
 __global__ void vq_tc_prep_kernel(const float *__restrict__ E, int K, int Kpad, float *__restrict__ bn,
@@ -90,7 +104,8 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, int K, int Kpad, 
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme, const VqTcParams p) {
+vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme,
+             const __grid_constant__ CUtensorMap tmq, const VqTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -111,10 +126,11 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     if (tid == 0) {
         ptx::prefetch_tmap(&tmz);
         ptx::prefetch_tmap(&tme);
+        ptx::prefetch_tmap(&tmq);
         ptx::mbar_init(bar(Z_FULL + 0), 1); ptx::mbar_init(bar(Z_FULL + 1), 1);
-        ptx::mbar_init(bar(Z_EMPTY + 0), 9); ptx::mbar_init(bar(Z_EMPTY + 1), 9);   // MMA commit + 8 epilogue warps
+        ptx::mbar_init(bar(Q_FULL + 0), 8); ptx::mbar_init(bar(Q_FULL + 1), 8);     // 8 epilogue warps
         ptx::mbar_init(bar(E_FULL + 0), 1); ptx::mbar_init(bar(E_FULL + 1), 1);
-        ptx::mbar_init(bar(E_EMPTY + 0), 9); ptx::mbar_init(bar(E_EMPTY + 1), 9);
+        ptx::mbar_init(bar(E_EMPTY + 0), 9); ptx::mbar_init(bar(E_EMPTY + 1), 9);   // MMA commit + 8 warps
         ptx::mbar_init(bar(T_FULL + 0), 1); ptx::mbar_init(bar(T_FULL + 1), 1);
         ptx::mbar_init(bar(T_EMPTY + 0), 8); ptx::mbar_init(bar(T_EMPTY + 1), 8);
         ptx::fence_mbar_init();
@@ -128,13 +144,27 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (+ z_q tile stores) =====================
         if (lane == 0) {
             long long gc = 0;
             int it = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            long long tile = blockIdx.x;
+            // a z stage is recycled once its tile's z_q (written in place by the epilogue)
+            // has been TMA-stored; Q_FULL also implies the MMAs of that tile are done.
+            auto drain = [&](int jt, long long jtile) {
+                const int zs = jt & 1;
+                ptx::mbar_wait(bar(Q_FULL + zs), (jt >> 1) & 1);
+                if (!(p.flags & 4)) {
+                    const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
+                    tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
+                    tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
+                    bulk_commit();
+                    bulk_wait_read0();
+                }
+            };
+            for (; tile < ntiles; tile += gridDim.x, ++it) {
                 const int zs = it & 1;
-                ptx::mbar_wait(bar(Z_EMPTY + zs), ((it >> 1) & 1) ^ 1);
+                if (it >= 2) drain(it - 2, tile - 2 * (long long)gridDim.x);
                 ptx::mbar_expect_tx(bar(Z_FULL + zs), ZSTAGE);
                 const uint32_t zdst = sbase + OFF_Z + zs * ZSTAGE;
                 ptx::tma_load_2d(zdst, &tmz, bar(Z_FULL + zs), 0, (int)(tile * TM));
@@ -151,6 +181,10 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
                 }
             }
+            // `it` tiles were issued; the last (up to) two are still to be stored
+            for (int jt = (it >= 2 ? it - 2 : 0); jt < it; ++jt)
+                drain(jt, (long long)blockIdx.x + (long long)jt * gridDim.x);
+            bulk_wait_all0();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -183,7 +217,6 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     ptx::tc_commit(bar(T_FULL + ab));
                     if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
                 }
-                ptx::tc_commit(bar(Z_EMPTY + zs));
             }
         }
     } else if (warp >= 4) {
@@ -192,17 +225,19 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int h = (warp - 4) >> 2;          // column half of every chunk
         const int row = q * 32 + lane;          // accumulator row = TMEM lane
+        const int rsw = row & 7;
         const float INF = __int_as_float(0x7f800000);
         const float Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
         const bool bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
         float2 *lists = reinterpret_cast<float2 *>(sm + OFF_LIST);
         float *xmin = reinterpret_cast<float *>(sm + OFF_XMIN);
+        int *xnc = reinterpret_cast<int *>(sm + OFF_XMIN);
         float *xbd = reinterpret_cast<float *>(sm + OFF_XBD);
         int *xbk = reinterpret_cast<int *>(sm + OFF_XBK);
         const int Kpad = nchunks * CN;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         double sse = 0.0;
 
-        // exact canonical distance of code k for this thread's row (zr in registers)
         auto code_ptr_smem = [&](int k) -> const unsigned char * {
             return sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128;
         };
@@ -210,32 +245,27 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
+            unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
             ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
-            float zr[DD];
-            {
-                const unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
-#pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16) {
-                        const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ (row & 7)) << 4));
-                        zr[a * 32 + c16 * 4 + 0] = v.x; zr[a * 32 + c16 * 4 + 1] = v.y;
-                        zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
-                    }
-            }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar(Z_EMPTY + zs));
 
-            float A = 0.f;                                    // quantizer.py:49, canonical order
+            // ---- A_i = sum_d fl(z^2), canonical left-to-right order (quantizer.py:49) ----
+            float A = 0.f;
 #pragma unroll
-            for (int d = 0; d < DD; ++d) A = __fadd_rn(A, __fmul_rn(zr[d], zr[d]));
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ rsw) << 4));
+                    A = __fadd_rn(A, __fmul_rn(v.x, v.x)); A = __fadd_rn(A, __fmul_rn(v.y, v.y));
+                    A = __fadd_rn(A, __fmul_rn(v.z, v.z)); A = __fadd_rn(A, __fmul_rn(v.w, v.w));
+                }
             // S >= sum_d |z_d e_kd| for every k (Cauchy-Schwarz, rounded up)
             const float S = sqrtf(A) * 1.00001f * Emax;
             // 2 x (tf32 truncation of both operands on 2M: 2*2^-9*S, + fp32 accumulation and
             // the canonical formula's own rounding), with margin.
             const float tau = S * (0.0078125f + 0.0009765625f) + (A + Emax * Emax + S) * 1.9073486e-6f;
-            const bool slow_row = bad_codebook || !(A < INF) || !(tau < INF);
+            bool slow_row = bad_codebook || !(A < INF) || !(tau < INF);
 
+            // ---- pass 1: approximate scores -> group minima -> candidate list ----
             float run_min = INF, thr = INF;
             int cnt = 0;
             for (int c = 0; c < nchunks; ++c) {
@@ -244,17 +274,15 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 const int es = resident ? c : (int)(gc & 1);
                 ptx::mbar_wait(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1));
                 ptx::tc_fence_after();
-                const float *bch = bsm + es * CN;
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const int col0 = h * 128 + j * 32;
-                    float v[32];
-                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * CN + col0), v);
-                    ptx::tmem_ld_wait();
+                const float *bch = bsm + es * CN + h * 128;
+                const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
+                const int gbase = (c * CN + h * 128) / 8;
+                float va[32], vb[32];
+                auto process = [&](const float (&v)[32], int j) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 b0 = *reinterpret_cast<const float4 *>(bch + col0 + g * 8);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(bch + col0 + g * 8 + 4);
+                        const float4 b0 = *reinterpret_cast<const float4 *>(bch + j * 32 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(bch + j * 32 + g * 8 + 4);
                         const float s0 = fmaf(v[g * 8 + 0], -2.f, b0.x), s1 = fmaf(v[g * 8 + 1], -2.f, b0.y);
                         const float s2 = fmaf(v[g * 8 + 2], -2.f, b0.z), s3 = fmaf(v[g * 8 + 3], -2.f, b0.w);
                         const float s4 = fmaf(v[g * 8 + 4], -2.f, b1.x), s5 = fmaf(v[g * 8 + 5], -2.f, b1.y);
@@ -262,19 +290,33 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         if (p.dbg) {
                             const long long grow = tile * TM + row;
                             if (grow < p.N) {
-                                float *dst = p.dbg + (size_t)grow * Kpad + c * CN + col0 + g * 8;
+                                float *dst = p.dbg + (size_t)grow * Kpad + c * CN + h * 128 + j * 32 + g * 8;
                                 dst[0] = s0; dst[1] = s1; dst[2] = s2; dst[3] = s3;
                                 dst[4] = s4; dst[5] = s5; dst[6] = s6; dst[7] = s7;
                             }
                         }
                         const float gm = ptx::fmin3(ptx::fmin3(s0, s1, s2), ptx::fmin3(s3, s4, s5), fminf(s6, s7));
                         if (gm <= thr) {
-                            if (cnt < LCAP) lists[cnt * 256 + et] = make_float2(gm, __int_as_float((c * CN + col0) / 8 + g));
+                            if (cnt < LCAP) lists[cnt * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
                             ++cnt;
                         }
                         run_min = fminf(run_min, gm);
                         thr = run_min + tau;
                     }
+                };
+                if (!(p.flags & 2)) {
+                    ptx::tmem_ld32(tcol, va);
+                    ptx::tmem_ld_wait32(va);
+                    ptx::tmem_ld32(tcol + 32, vb);
+                    process(va, 0);
+                    ptx::tmem_ld_wait32(vb);
+                    ptx::tmem_ld32(tcol + 64, va);
+                    process(vb, 1);
+                    ptx::tmem_ld_wait32(va);
+                    ptx::tmem_ld32(tcol + 96, vb);
+                    process(va, 2);
+                    ptx::tmem_ld_wait32(vb);
+                    process(vb, 3);
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -289,56 +331,116 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             ptx::named_bar_sync(1 + q, 64);
             thr = fminf(run_min, xmin[et ^ 128]) + tau;
 
-            // ---- exact canonical re-scoring of the candidate groups ----
+            // ---- filter the list down to the groups that can hold the canonical winner ----
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nc = 0;
+            if (cnt > LCAP) slow_row = true;
+            if (!slow_row) {
+                for (int s = 0; s < cnt; ++s) {
+                    const float2 ent = lists[s * 256 + et];
+                    if (ent.x <= thr) {
+                        const int g = __float_as_int(ent.y);
+                        if (nc == 0) c0 = g; else if (nc == 1) c1 = g; else if (nc == 2) c2 = g; else c3 = g;
+                        ++nc;
+                    }
+                }
+                if (nc > CMAX) slow_row = true;
+            }
+            // candidates travel to the partner through this thread's OWN last two list slots
+            // (no other thread ever touches them), the count through xnc (aliases xmin, hence
+            // the extra barrier: the partner must have read xmin first).
+            ptx::named_bar_sync(1 + q, 64);
+            lists[(LCAP - 2) * 256 + et] = make_float2(__int_as_float(c0), __int_as_float(c1));
+            lists[(LCAP - 1) * 256 + et] = make_float2(__int_as_float(c2), __int_as_float(c3));
+            xnc[et] = slow_row ? -1 : nc;
+            ptx::named_bar_sync(1 + q, 64);
+            const int pnc = xnc[et ^ 128];
+            int4 pc;
+            {
+                const float2 lo = lists[(LCAP - 2) * 256 + (et ^ 128)], hi = lists[(LCAP - 1) * 256 + (et ^ 128)];
+                pc = make_int4(__float_as_int(lo.x), __float_as_int(lo.y), __float_as_int(hi.x), __float_as_int(hi.y));
+            }
+            if (pnc < 0) slow_row = true;
+
+            // ---- z row -> registers (needed for the exact chains and for z_q) ----
+            float zr[DD];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ rsw) << 4));
+                    zr[a * 32 + c16 * 4 + 0] = v.x; zr[a * 32 + c16 * 4 + 1] = v.y;
+                    zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
+                }
+
+            // ---- exact canonical re-scoring ----
             float bd = 0.f;
             int bk = -1;
-            auto rescore = [&](int k) {
-                float M = 0.f, bnk;
+            auto consider = [&](float M, int k) {
+                if (k < p.K) {
+                    const float bnk = resident ? bsm[k] : __ldg(p.bn + k);
+                    const float dist = __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));   // quantizer.py:49-51
+                    if (bk < 0 || vq_better(dist, k, bd, bk)) { bd = dist; bk = k; }
+                }
+            };
+            // four codes k0..k0+3 at once: four independent sequential fmaf chains
+            auto rescore4 = [&](int k0) {
+                float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3 = 0.f;
                 if (resident) {
-                    const unsigned char *er = code_ptr_smem(k);
-                    const int sw = k & 7;
+                    const unsigned char *er = code_ptr_smem(k0);      // k0 % 4 == 0: same 8-row swizzle group
+                    const int sw = k0 & 7;
 #pragma unroll
                     for (int a = 0; a < 2; ++a)
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {
-                            const float4 e4 = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ sw) << 4));
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 0], e4.x, M);
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 1], e4.y, M);
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 2], e4.z, M);
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 3], e4.w, M);
+                            const float4 e0 = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ sw) << 4));
+                            const float4 e1 = *reinterpret_cast<const float4 *>(er + 128 + a * EATOM + ((c16 ^ (sw + 1)) << 4));
+                            const float4 e2 = *reinterpret_cast<const float4 *>(er + 256 + a * EATOM + ((c16 ^ (sw + 2)) << 4));
+                            const float4 e3 = *reinterpret_cast<const float4 *>(er + 384 + a * EATOM + ((c16 ^ (sw + 3)) << 4));
+                            const float z0 = zr[a * 32 + c16 * 4 + 0], z1 = zr[a * 32 + c16 * 4 + 1];
+                            const float z2 = zr[a * 32 + c16 * 4 + 2], z3 = zr[a * 32 + c16 * 4 + 3];
+                            M0 = __fmaf_rn(z0, e0.x, M0); M1 = __fmaf_rn(z0, e1.x, M1); M2 = __fmaf_rn(z0, e2.x, M2); M3 = __fmaf_rn(z0, e3.x, M3);
+                            M0 = __fmaf_rn(z1, e0.y, M0); M1 = __fmaf_rn(z1, e1.y, M1); M2 = __fmaf_rn(z1, e2.y, M2); M3 = __fmaf_rn(z1, e3.y, M3);
+                            M0 = __fmaf_rn(z2, e0.z, M0); M1 = __fmaf_rn(z2, e1.z, M1); M2 = __fmaf_rn(z2, e2.z, M2); M3 = __fmaf_rn(z2, e3.z, M3);
+                            M0 = __fmaf_rn(z3, e0.w, M0); M1 = __fmaf_rn(z3, e1.w, M1); M2 = __fmaf_rn(z3, e2.w, M2); M3 = __fmaf_rn(z3, e3.w, M3);
                         }
-                    bnk = bsm[k];
                 } else {
-                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);
+                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k0 * DD);
+                    const bool v1 = k0 + 1 < p.K, v2 = k0 + 2 < p.K, v3 = k0 + 3 < p.K;
+                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int c16 = 0; c16 < 16; ++c16) {
-                        const float4 e4 = __ldg(er + c16);
-                        M = __fmaf_rn(zr[c16 * 4 + 0], e4.x, M);
-                        M = __fmaf_rn(zr[c16 * 4 + 1], e4.y, M);
-                        M = __fmaf_rn(zr[c16 * 4 + 2], e4.z, M);
-                        M = __fmaf_rn(zr[c16 * 4 + 3], e4.w, M);
+                        const float4 e0 = __ldg(er + c16);
+                        const float4 e1 = v1 ? __ldg(er + 16 + c16) : zero4;
+                        const float4 e2 = v2 ? __ldg(er + 32 + c16) : zero4;
+                        const float4 e3 = v3 ? __ldg(er + 48 + c16) : zero4;
+                        const float z0 = zr[c16 * 4 + 0], z1 = zr[c16 * 4 + 1], z2 = zr[c16 * 4 + 2], z3 = zr[c16 * 4 + 3];
+                        M0 = __fmaf_rn(z0, e0.x, M0); M1 = __fmaf_rn(z0, e1.x, M1); M2 = __fmaf_rn(z0, e2.x, M2); M3 = __fmaf_rn(z0, e3.x, M3);
+                        M0 = __fmaf_rn(z1, e0.y, M0); M1 = __fmaf_rn(z1, e1.y, M1); M2 = __fmaf_rn(z1, e2.y, M2); M3 = __fmaf_rn(z1, e3.y, M3);
+                        M0 = __fmaf_rn(z2, e0.z, M0); M1 = __fmaf_rn(z2, e1.z, M1); M2 = __fmaf_rn(z2, e2.z, M2); M3 = __fmaf_rn(z2, e3.z, M3);
+                        M0 = __fmaf_rn(z3, e0.w, M0); M1 = __fmaf_rn(z3, e1.w, M1); M2 = __fmaf_rn(z3, e2.w, M2); M3 = __fmaf_rn(z3, e3.w, M3);
                     }
-                    bnk = __ldg(p.bn + k);
                 }
-                const float dist = __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));   // quantizer.py:49-51
-                if (bk < 0 || vq_better(dist, k, bd, bk)) { bd = dist; bk = k; }
+                consider(M0, k0); consider(M1, k0 + 1); consider(M2, k0 + 2); consider(M3, k0 + 3);
             };
-            if (!slow_row && cnt <= LCAP) {
-                for (int s = 0; s < cnt; ++s) {
-                    const float2 ent = lists[s * 256 + et];
-                    if (ent.x <= thr) {
-                        const int k0 = __float_as_int(ent.y) * 8;
-#pragma unroll 1
-                        for (int j = 0; j < 8; ++j)
-                            if (k0 + j < p.K) rescore(k0 + j);
-                    }
+            if (p.flags & 1) {
+                bk = (nc > 0) ? c0 * 8 : ((pnc > 0) ? pc.x * 8 : 0);    // timing experiment only
+            } else if (!slow_row) {
+                // both threads of the row walk the union of the two lists; each takes 4 of the 8 codes
+                const int total = nc + pnc;
+                for (int t = 0; t < total; ++t) {
+                    int g;
+                    if (t < nc) g = (t == 0) ? c0 : (t == 1) ? c1 : (t == 2) ? c2 : c3;
+                    else { const int u = t - nc; g = (u == 0) ? pc.x : (u == 1) ? pc.y : (u == 2) ? pc.z : pc.w; }
+                    const int k0 = g * 8 + h * 4;
+                    if (k0 < p.K) rescore4(k0);
                 }
             } else {
-                // non-finite data or list overflow (e.g. many duplicated codes): scan every code
+                // non-finite data or overflowing lists (e.g. many duplicated codes): scan this
+                // thread's half of every chunk exactly
                 for (int c = 0; c < nchunks; ++c)
-                    for (int kk = 0; kk < 128; ++kk) {
-                        const int k = c * CN + h * 128 + kk;
-                        if (k < p.K) rescore(k);
+                    for (int kk = 0; kk < 128; kk += 4) {
+                        const int k0 = c * CN + h * 128 + kk;
+                        if (k0 < p.K) rescore4(k0);
                     }
             }
             xbd[et] = bd;
@@ -350,10 +452,9 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 if (ok >= 0 && (bk < 0 || vq_better(od, ok, bd, bk))) { bd = od; bk = ok; }
             }
 
-            // ---- gather e_idx, straight-through z_q, SSE, histogram (this thread: 32 of 64 dims) ----
+            // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram ----
             const long long grow = tile * TM + row;
-            if (grow < p.N) {
-                float *qdst = p.zq + (size_t)grow * DD + h * 32;
+            {
                 auto emit = [&](const float *zh) {
 #pragma unroll
                     for (int c16 = 0; c16 < 8; ++c16) {
@@ -367,19 +468,25 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         df.z = __fsub_rn(e4.z, zh[c16 * 4 + 2]); df.w = __fsub_rn(e4.w, zh[c16 * 4 + 3]);
                         o.x = __fadd_rn(zh[c16 * 4 + 0], df.x); o.y = __fadd_rn(zh[c16 * 4 + 1], df.y);   // quantizer.py:67
                         o.z = __fadd_rn(zh[c16 * 4 + 2], df.z); o.w = __fadd_rn(zh[c16 * 4 + 3], df.w);
-                        *reinterpret_cast<float4 *>(qdst + c16 * 4) = o;
-                        sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
+                        *reinterpret_cast<float4 *>(zrow + h * ZATOM + ((c16 ^ rsw) << 4)) = o;
+                        if (grow < p.N)
+                            sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
                     }
                 };
                 if (h == 0) {
                     emit(zr);
-                    p.idx[grow] = bk;
-                    if (smem_hist) atomicAdd(&hist_s[bk], 1);
-                    else atomicAdd(&p.hist[bk], 1);
+                    if (grow < p.N) {
+                        p.idx[grow] = bk;
+                        if (smem_hist) atomicAdd(&hist_s[bk], 1);
+                        else atomicAdd(&p.hist[bk], 1);
+                    }
                 } else {
                     emit(zr + 32);
                 }
             }
+            ptx::fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(Q_FULL + zs));
         }
 
         // ---- CTA reduction of the SSE partial, histogram flush ----
@@ -442,11 +549,14 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     unsigned *scal = reinterpret_cast<unsigned *>(w + align256((size_t)Kpad * 4));
     double *partials = reinterpret_cast<double *>(w + align256((size_t)Kpad * 4) + 256);
 
-    CUtensorMap tmz, tme;
+    CUtensorMap tmz, tme, tmq;
     int rc = vqb_encode_tmap_2d(&tmz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, z, DD, (uint64_t)N, DD * 4, 32, TM,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = vqb_encode_tmap_2d(&tme, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, E, DD, (uint64_t)K, DD * 4, 32, CN,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, zq, DD, (uint64_t)N, DD * 4, 32, TM,
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
@@ -471,8 +581,12 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     VqTcParams p;
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
-    p.idx = idx; p.zq = zq; p.partials = partials; p.hist = hist; p.dbg = dbg;
-    vq_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, p);
+    p.idx = idx; p.partials = partials; p.hist = hist; p.dbg = dbg;
+    {
+        const char *fl = getenv("VQB_TC_FLAGS");
+        p.flags = fl ? atoi(fl) : 0;
+    }
+    vq_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
     VQB_COUNT_LAUNCH(3);
     return vqb_cuda_status(cudaGetLastError());
