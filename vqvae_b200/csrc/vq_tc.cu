@@ -296,10 +296,9 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                             }
                         }
                         const float gm = ptx::fmin3(ptx::fmin3(s0, s1, s2), ptx::fmin3(s3, s4, s5), fminf(s6, s7));
-                        if (gm <= thr) {
-                            if (cnt < LCAP) lists[cnt * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
-                            ++cnt;
-                        }
+                        // branch-free push: always write slot min(cnt, LCAP-1), keep it when in range
+                        lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
+                        cnt += (gm <= thr) ? 1 : 0;
                         run_min = fminf(run_min, gm);
                         thr = run_min + tau;
                     }
@@ -333,7 +332,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
 
             // ---- filter the list down to the groups that can hold the canonical winner ----
             int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nc = 0;
-            if (cnt > LCAP) slow_row = true;
+            if (cnt >= LCAP) slow_row = true;      // slot LCAP-1 is the scratch slot of the branch-free push
             if (!slow_row) {
                 for (int s = 0; s < cnt; ++s) {
                     const float2 ent = lists[s * 256 + et];
@@ -382,20 +381,27 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     if (bk < 0 || vq_better(dist, k, bd, bk)) { bd = dist; bk = k; }
                 }
             };
-            // four codes k0..k0+3 at once: four independent sequential fmaf chains
-            auto rescore4 = [&](int k0) {
-                float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3 = 0.f;
+            // This thread's four codes of an 8-code group.  Roles are rotated per lane so that at
+            // every load the 32 lanes of a warp spread evenly over the eight 16-byte bank groups
+            // of the swizzled rows (row k keeps chunk c16 at position c16 ^ (k & 7)); the partner
+            // thread (same lane, other column half) takes the complementary four codes.
+            const int jbase = 4 * (h ^ (lane & 1)), jrot = lane >> 1;
+            const int j0 = jbase + ((jrot + 0) & 3), j1 = jbase + ((jrot + 1) & 3);
+            const int j2 = jbase + ((jrot + 2) & 3), j3 = jbase + ((jrot + 3) & 3);
+            auto rescore_group = [&](int g) {
+                const int kg = g * 8;
+                float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3 = 0.f;     // four independent sequential chains
                 if (resident) {
-                    const unsigned char *er = code_ptr_smem(k0);      // k0 % 4 == 0: same 8-row swizzle group
-                    const int sw = k0 & 7;
+                    const unsigned char *eg = code_ptr_smem(kg);
+                    const unsigned char *r0 = eg + j0 * 128, *r1 = eg + j1 * 128, *r2 = eg + j2 * 128, *r3 = eg + j3 * 128;
 #pragma unroll
                     for (int a = 0; a < 2; ++a)
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {
-                            const float4 e0 = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ sw) << 4));
-                            const float4 e1 = *reinterpret_cast<const float4 *>(er + 128 + a * EATOM + ((c16 ^ (sw + 1)) << 4));
-                            const float4 e2 = *reinterpret_cast<const float4 *>(er + 256 + a * EATOM + ((c16 ^ (sw + 2)) << 4));
-                            const float4 e3 = *reinterpret_cast<const float4 *>(er + 384 + a * EATOM + ((c16 ^ (sw + 3)) << 4));
+                            const float4 e0 = *reinterpret_cast<const float4 *>(r0 + a * EATOM + ((c16 ^ j0) << 4));
+                            const float4 e1 = *reinterpret_cast<const float4 *>(r1 + a * EATOM + ((c16 ^ j1) << 4));
+                            const float4 e2 = *reinterpret_cast<const float4 *>(r2 + a * EATOM + ((c16 ^ j2) << 4));
+                            const float4 e3 = *reinterpret_cast<const float4 *>(r3 + a * EATOM + ((c16 ^ j3) << 4));
                             const float z0 = zr[a * 32 + c16 * 4 + 0], z1 = zr[a * 32 + c16 * 4 + 1];
                             const float z2 = zr[a * 32 + c16 * 4 + 2], z3 = zr[a * 32 + c16 * 4 + 3];
                             M0 = __fmaf_rn(z0, e0.x, M0); M1 = __fmaf_rn(z0, e1.x, M1); M2 = __fmaf_rn(z0, e2.x, M2); M3 = __fmaf_rn(z0, e3.x, M3);
@@ -404,15 +410,14 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                             M0 = __fmaf_rn(z3, e0.w, M0); M1 = __fmaf_rn(z3, e1.w, M1); M2 = __fmaf_rn(z3, e2.w, M2); M3 = __fmaf_rn(z3, e3.w, M3);
                         }
                 } else {
-                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k0 * DD);
-                    const bool v1 = k0 + 1 < p.K, v2 = k0 + 2 < p.K, v3 = k0 + 3 < p.K;
-                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int kl = p.K - 1;     // clamp the address; consider() drops k >= K
+                    const float4 *r0 = reinterpret_cast<const float4 *>(p.E + (size_t)min(kg + j0, kl) * DD);
+                    const float4 *r1 = reinterpret_cast<const float4 *>(p.E + (size_t)min(kg + j1, kl) * DD);
+                    const float4 *r2 = reinterpret_cast<const float4 *>(p.E + (size_t)min(kg + j2, kl) * DD);
+                    const float4 *r3 = reinterpret_cast<const float4 *>(p.E + (size_t)min(kg + j3, kl) * DD);
 #pragma unroll
                     for (int c16 = 0; c16 < 16; ++c16) {
-                        const float4 e0 = __ldg(er + c16);
-                        const float4 e1 = v1 ? __ldg(er + 16 + c16) : zero4;
-                        const float4 e2 = v2 ? __ldg(er + 32 + c16) : zero4;
-                        const float4 e3 = v3 ? __ldg(er + 48 + c16) : zero4;
+                        const float4 e0 = __ldg(r0 + c16), e1 = __ldg(r1 + c16), e2 = __ldg(r2 + c16), e3 = __ldg(r3 + c16);
                         const float z0 = zr[c16 * 4 + 0], z1 = zr[c16 * 4 + 1], z2 = zr[c16 * 4 + 2], z3 = zr[c16 * 4 + 3];
                         M0 = __fmaf_rn(z0, e0.x, M0); M1 = __fmaf_rn(z0, e1.x, M1); M2 = __fmaf_rn(z0, e2.x, M2); M3 = __fmaf_rn(z0, e3.x, M3);
                         M0 = __fmaf_rn(z1, e0.y, M0); M1 = __fmaf_rn(z1, e1.y, M1); M2 = __fmaf_rn(z1, e2.y, M2); M3 = __fmaf_rn(z1, e3.y, M3);
@@ -420,7 +425,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         M0 = __fmaf_rn(z3, e0.w, M0); M1 = __fmaf_rn(z3, e1.w, M1); M2 = __fmaf_rn(z3, e2.w, M2); M3 = __fmaf_rn(z3, e3.w, M3);
                     }
                 }
-                consider(M0, k0); consider(M1, k0 + 1); consider(M2, k0 + 2); consider(M3, k0 + 3);
+                consider(M0, kg + j0); consider(M1, kg + j1); consider(M2, kg + j2); consider(M3, kg + j3);
             };
             if (p.flags & 1) {
                 bk = (nc > 0) ? c0 * 8 : ((pnc > 0) ? pc.x * 8 : 0);    // timing experiment only
@@ -431,17 +436,11 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     int g;
                     if (t < nc) g = (t == 0) ? c0 : (t == 1) ? c1 : (t == 2) ? c2 : c3;
                     else { const int u = t - nc; g = (u == 0) ? pc.x : (u == 1) ? pc.y : (u == 2) ? pc.z : pc.w; }
-                    const int k0 = g * 8 + h * 4;
-                    if (k0 < p.K) rescore4(k0);
+                    if (g * 8 < p.K) rescore_group(g);
                 }
             } else {
-                // non-finite data or overflowing lists (e.g. many duplicated codes): scan this
-                // thread's half of every chunk exactly
-                for (int c = 0; c < nchunks; ++c)
-                    for (int kk = 0; kk < 128; kk += 4) {
-                        const int k0 = c * CN + h * 128 + kk;
-                        if (k0 < p.K) rescore4(k0);
-                    }
+                // non-finite data or overflowing lists (e.g. many duplicated codes): every code, exactly
+                for (int g = 0; g * 8 < p.K; ++g) rescore_group(g);
             }
             xbd[et] = bd;
             xbk[et] = bk;
