@@ -63,7 +63,9 @@ unsigned long long vqb_launch_count(void);
  * nn.Conv2d weight (Cout,Cin,kh,kw)          encoder.py:29-36, residual.py:20-24,
  *                                            vqvae.py:16-17
  * nn.ConvTranspose2d weight (Cin,Cout,kh,kw) decoder.py:28-35   (transposed = 1)
- * -> tap-major GEMM operand packed[(r*kw+s)*Cin + ci][co], fp32.                */
+ * -> `packed` holds 2*Cout*Cin*kh*kw floats: the tap-major GEMM operand in both
+ *    layouts the kernels read, [(r*kw+s)*Cin + ci][co] (FFMA path) followed by
+ *    [(r*kw+s)][co][ci] (K-major rows for the tcgen05 path).                      */
 int vqb_pack_conv_weight_f32(const float *w, float *packed, int Cout, int Cin, int kh,
                              int kw, int transposed, void *stream);
 

@@ -10,6 +10,9 @@ bool vq_tc_supported(long long N, int K, int D);
 int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
                  int *hist, void *ws, float *dbg, cudaStream_t s);
 
+bool conv_tc_supported(const ConvLaunch &p);
+int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaStream_t s);
+
 unsigned long long g_vqb_launches = 0;
 static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel
 extern "C" int vqb_set_vq_kernel(int which) {
@@ -79,6 +82,8 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
     set_strides(in_layout, Cin, H, W, p.in_sn, p.in_sh, p.in_sw, p.in_sc);
     set_strides(out_layout, Cout, OH, OW, p.out_sn, p.out_sh, p.out_sw, p.out_sc);
     const bool small = (Cout <= 4);
+    const float *w_tc = w_packed + (size_t)kh * kw * Cin * Cout;   // K-major copy for the tcgen05 path
+    const bool want_tc = precision != VQB_FP32;
 
     if (!transposed || stride == 1) {
         p.OHg = OH; p.OWg = OW;
@@ -92,6 +97,7 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 p.tap_dy[t] = transposed ? pad - r : r - pad;
                 p.tap_dx[t] = transposed ? pad - c : c - pad;
             }
+        if (want_tc && conv_tc_supported(p)) return launch_conv_tc(p, w_tc, kh * kw, s);
         return small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
     }
     // stride-s transposed conv: s*s sub-pixel phases, each a stride-1 gather conv
@@ -120,7 +126,8 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 // a phase no tap reaches still gets bias/skip/activation
                 p.ntaps = 0;
             }
-            rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
+            if (want_tc && nt > 0 && conv_tc_supported(p)) rc = launch_conv_tc(p, w_tc, kh * kw, s);
+            else rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
             if (rc != 0) return rc;
         }
     return 0;

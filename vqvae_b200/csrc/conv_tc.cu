@@ -1,0 +1,220 @@
+// conv_tc.cu -- tcgen05 implicit-GEMM convolution for sm_100a (VQB_TF32 arithmetic).
+//
+// Replaces the nn.Conv2d / nn.ConvTranspose2d call sites of the hot path whose channel
+// counts fill a tensor-core tile: encoder.py:32-36 (64->128 k4s2, 128->128 k3),
+// residual.py:20-24 (128->32 k3, 32->128 k1 + skip), vqvae.py:16-17 (128->64 k1),
+// decoder.py:28-33 (ConvT 64->128 k3s1, ConvT 128->64 k4s2 as four sub-pixel phases).
+//
+// GEMM view (one CTA = one 128-pixel output tile, all Cout columns):
+//   D[128 px][Cout] = sum over (tap t, 32-channel chunk c) A_t,c[128 px][32] * W_t,c[Cout][32]^T
+//   * A_t,c is fetched by ONE 4-D TMA box {32 ch, BW, BH, BN} of the NHWC input, shifted
+//     by the tap offset (dy,dx): the box lands in shared memory as 128 rows of 128 bytes
+//     in the 128-byte-swizzled K-major layout UMMA reads; out-of-image pixels are
+//     zero-filled by TMA (= the convolution's zero padding) and stride-2 convolutions use
+//     the tensor map's element strides.  Nothing like an im2col matrix ever exists.
+//   * W_t,c is a 2-D TMA box {32 ch, Cout} of the tap-major packed weight [t][Cout][Cin].
+//   * warp 0 = TMA producer, warp 1 = tcgen05.mma kind::tf32 issuer (fp32 accumulators
+//     in TMEM), warp 2 = TMEM allocator, warps 4-7 = epilogue: tcgen05.ld -> +bias
+//     -> +skip -> ReLU -> coalesced 16-byte NHWC stores.  3-stage mbarrier ring.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int CT_THREADS = 256;
+constexpr int CT_STAGES = 3;
+constexpr int A_BYTES = 128 * 128;                 // 128 pixels x 32 fp32
+
+struct ConvTcParams {
+    const float *bias, *skip;
+    float *out;
+    int B, Cin, Cout;
+    int OHg, OWg;                                  // output grid of this launch
+    int BW, BH, BN;                                // tile = BN images x BH rows x BW cols = 128 pixels
+    int tiles_x, tiles_y;
+    int in_step, out_step, out_py, out_px;
+    int ntaps;
+    int tap_w[VQB_MAX_TAPS], tap_dy[VQB_MAX_TAPS], tap_dx[VQB_MAX_TAPS];
+    long long out_sn, out_sh, out_sw;              // NHWC element strides of out / skip
+    int relu;
+};
+
+__global__ void __launch_bounds__(CT_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
+               const ConvTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+    const int b_bytes = p.Cout * 128;
+    const int stage_bytes = A_BYTES + b_bytes;
+    const uint32_t bars = sbase + CT_STAGES * stage_bytes;      // full[S], empty[S], tfull
+    float *bias_s = reinterpret_cast<float *>(sm + CT_STAGES * stage_bytes + 64);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + CT_STAGES * stage_bytes + 56);
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (CT_STAGES + s); };
+    const uint32_t tfull = bars + 8u * (2 * CT_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int tcols = 32;
+    while (tcols < p.Cout) tcols <<= 1;
+
+    // tile origin
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int gx0 = tx * p.BW, gy0 = ty * p.BH, n0 = tile * p.BN;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tma_in);
+        ptx::prefetch_tmap(&tma_w);
+        for (int s = 0; s < CT_STAGES; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+        ptx::mbar_init(tfull, 1);
+        ptx::fence_mbar_init();
+    }
+    for (int c = tid; c < p.Cout; c += CT_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    if (warp == 2) ptx::tmem_alloc(sbase + CT_STAGES * stage_bytes + 56, (uint32_t)tcols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int kchunks = p.Cin / 32;
+    const int ksteps = p.ntaps * kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % CT_STAGES;
+                const uint32_t ph = (uint32_t)((i / CT_STAGES) & 1);
+                const int t = i / kchunks, cc = i - t * kchunks;
+                ptx::mbar_wait(empty(s), ph ^ 1);
+                ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
+                const uint32_t dst = sbase + s * stage_bytes;
+                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 * p.in_step + p.tap_dx[t],
+                                 gy0 * p.in_step + p.tap_dy[t], n0);
+                ptx::tma_load_2d(dst + A_BYTES, &tma_w, full(s), cc * 32, p.tap_w[t] * p.Cout);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % CT_STAGES;
+                const uint32_t ph = (uint32_t)((i / CT_STAGES) & 1);
+                ptx::mbar_wait(full(s), ph);
+                ptx::tc_fence_after();
+                const uint32_t a = sbase + s * stage_bytes, b = a + A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128(a + kk * 32), ptx::smem_desc_sw128(b + kk * 32),
+                                  idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                ptx::tc_commit(empty(s));
+            }
+            ptx::tc_commit(tfull);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: this thread owns output pixel `row` of the tile ----
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+        const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
+        const bool valid = gx < p.OWg && gy < p.OHg && n < p.B;
+        const long long ob = (long long)n * p.out_sn + (long long)(gy * p.out_step + p.out_py) * p.out_sh +
+                             (long long)(gx * p.out_step + p.out_px) * p.out_sw;
+        if (ksteps > 0) {
+            ptx::mbar_wait(tfull, 0);
+            ptx::tc_fence_after();
+        }
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            float v[32];
+            if (ksteps > 0) {
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                ptx::tmem_ld_wait32(v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (c0 + i < p.Cout) {             // Cout % 16 == 0: whole float4s
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
+                        float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                        if (p.skip) {
+                            const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
+                            o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                        }
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+}
+
+int pow2_ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvLaunch &p) {
+    const bool in_nhwc = p.in_sc == 1 && p.in_sw == p.Cin;
+    const bool out_nhwc = p.out_sc == 1 && p.out_sw == p.Cout;
+    return in_nhwc && out_nhwc && p.Cin % 32 == 0 && p.Cout % 16 == 0 && p.Cout >= 16 && p.Cout <= 256 &&
+           p.in_step >= 1 && p.in_step <= 2 && p.ntaps >= 1 &&
+           (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+           (p.skip == nullptr || (reinterpret_cast<uintptr_t>(p.skip) & 15) == 0);
+}
+
+// w_tc: tap-major K-major weight [tap][Cout][Cin] (vqb_pack_conv_weight_f32, second half)
+int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaStream_t s) {
+    ConvTcParams q;
+    q.bias = p.bias; q.skip = p.skip; q.out = p.out;
+    q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout; q.OHg = p.OHg; q.OWg = p.OWg;
+    q.BW = pow2_ceil(p.OWg) < 16 ? pow2_ceil(p.OWg) : 16;
+    q.BH = pow2_ceil(p.OHg) < 128 / q.BW ? pow2_ceil(p.OHg) : 128 / q.BW;
+    q.BN = 128 / (q.BW * q.BH);
+    q.tiles_x = (p.OWg + q.BW - 1) / q.BW;
+    q.tiles_y = (p.OHg + q.BH - 1) / q.BH;
+    const int tiles_n = (p.B + q.BN - 1) / q.BN;
+    q.in_step = p.in_step; q.out_step = p.out_step; q.out_py = p.out_py; q.out_px = p.out_px;
+    q.ntaps = p.ntaps;
+    for (int t = 0; t < p.ntaps; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
+    q.out_sn = p.out_sn; q.out_sh = p.out_sh; q.out_sw = p.out_sw; q.relu = p.relu;
+
+    CUtensorMap tin, tw;
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    const uint64_t strides[3] = {(uint64_t)p.Cin * 4, (uint64_t)p.W * p.Cin * 4, (uint64_t)p.H * p.W * p.Cin * 4};
+    const uint32_t box[4] = {32u, (uint32_t)(q.BW * p.in_step), (uint32_t)(q.BH * p.in_step), (uint32_t)q.BN};
+    const uint32_t es[4] = {1u, (uint32_t)p.in_step, (uint32_t)p.in_step, 1u};
+    int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.in, dims, strides, box, es,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, w_tc, (uint64_t)p.Cin,
+                            (uint64_t)total_taps * p.Cout, (uint64_t)p.Cin * 4, 32, (uint32_t)p.Cout,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int stage_bytes = A_BYTES + p.Cout * 128;
+    const int smem = CT_STAGES * stage_bytes + 64 + p.Cout * 4 + 1024;
+    static int attr_max = 0;
+    if (smem > attr_max) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_max = smem;
+    }
+    const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
+    if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    conv_tc_kernel<<<(unsigned)grid, CT_THREADS, smem, s>>>(tin, tw, q);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}

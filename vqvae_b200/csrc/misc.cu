@@ -3,7 +3,9 @@
 
 namespace {
 
-// (Cout,Cin,kh,kw) or ConvTranspose (Cin,Cout,kh,kw)  ->  [(r*kw+s)*Cin + ci][co]
+// (Cout,Cin,kh,kw) or ConvTranspose (Cin,Cout,kh,kw)  ->  two GEMM operand layouts, back to back:
+//   out[0 .. T)        [(r*kw+s)*Cin + ci][co]   (N-major, the FFMA kernel's B tile)
+//   out[T .. 2T)       [(r*kw+s)][co][ci]        (K-major rows of Cin, the tcgen05 B operand)
 __global__ void pack_weight_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin,
                                    int kh, int kw, int transposed) {
     const long long total = (long long)Cout * Cin * kh * kw;
@@ -16,7 +18,9 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, float *__restric
         const int r = tap / kw, s = tap % kw;
         const long long src = transposed ? ((((long long)ci * Cout + co) * kh + r) * kw + s)
                                          : ((((long long)co * Cin + ci) * kh + r) * kw + s);
-        out[i] = w[src];
+        const float v = w[src];
+        out[i] = v;
+        out[total + ((long long)tap * Cout + co) * Cin + ci] = v;
     }
 }
 

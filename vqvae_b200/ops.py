@@ -54,15 +54,16 @@ def _f32c(t):
 
 
 def pack_conv_weight(w, transposed):
-    """(Cout,Cin,kh,kw) conv / (Cin,Cout,kh,kw) conv-transpose weight -> tap-major
-    fp32 GEMM operand [(r*kw+s)*Cin+ci][co] (vqb_pack_conv_weight_f32)."""
+    """(Cout,Cin,kh,kw) conv / (Cin,Cout,kh,kw) conv-transpose weight -> the two tap-major
+    fp32 GEMM operand layouts of vqb_pack_conv_weight_f32, back to back:
+    [(r*kw+s)*Cin+ci][co] for the FFMA kernel and [(r*kw+s)][co][ci] for tcgen05."""
     _require_cuda(w, "weight")
     w = _f32c(w.detach())
     if transposed:
         cin, cout, kh, kw = w.shape
     else:
         cout, cin, kh, kw = w.shape
-    out = torch.empty((kh * kw * cin, cout), dtype=torch.float32, device=w.device)
+    out = torch.empty((2, kh * kw * cin * cout), dtype=torch.float32, device=w.device)
     check(lib().vqb_pack_conv_weight_f32(w.data_ptr(), out.data_ptr(), cout, cin, kh, kw,
                                          int(bool(transposed)), _stream()), "pack_conv_weight")
     return out
