@@ -10,8 +10,12 @@ bool vq_tc_supported(long long N, int K, int D);
 int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
                  int *hist, void *ws, float *dbg, cudaStream_t s);
 
+int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
+                        int Cout, int relu, cudaStream_t s);
+int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
+                          int Cout, int relu, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
-int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaStream_t s);
+int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
 
 unsigned long long g_vqb_launches = 0;
 static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel
@@ -76,6 +80,16 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
     const int OW = transposed ? (W - 1) * stride - 2 * pad + kw : (W + 2 * pad - kw) / stride + 1;
     if (OH <= 0 || OW <= 0) return VQB_ERR_BAD_ARG;
 
+    // the two HBM-bound end layers have dedicated kernels (conv_edge.cu)
+    if (kh == 4 && kw == 4 && stride == 2 && pad == 1 && !skip) {
+        if (!transposed && Cin == 3 && Cout % 32 == 0 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
+            H % 2 == 0 && W % 2 == 0 && (size_t)16 * Cin * Cout * 4 <= 48 * 1024)
+            return launch_conv_in_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
+        if (transposed && Cout == 3 && Cin % 4 == 0 && in_layout == VQB_NHWC && out_layout == VQB_NCHW &&
+            (size_t)16 * Cin * 16 <= 48 * 1024)
+            return launch_convt_out_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
+    }
+
     ConvLaunch p;
     p.in = in; p.w = w_packed; p.bias = bias; p.skip = skip; p.out = out;
     p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
@@ -97,12 +111,15 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 p.tap_dy[t] = transposed ? pad - r : r - pad;
                 p.tap_dx[t] = transposed ? pad - c : c - pad;
             }
-        if (want_tc && conv_tc_supported(p)) return launch_conv_tc(p, w_tc, kh * kw, s);
+        if (want_tc && conv_tc_supported(p)) return launch_conv_tc(&p, 1, w_tc, kh * kw, s);
         return small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
     }
     // stride-s transposed conv: s*s sub-pixel phases, each a stride-1 gather conv
     // over the taps whose parity matches (decoder.py:31-35).
     p.in_step = 1; p.out_step = stride;
+    ConvLaunch phases[4];
+    int nph = 0;
+    const bool tc_multi = want_tc && stride == 2 && conv_tc_supported(p);
     for (int py = 0; py < stride; ++py)
         for (int px = 0; px < stride; ++px) {
             p.out_py = py; p.out_px = px;
@@ -126,10 +143,11 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 // a phase no tap reaches still gets bias/skip/activation
                 p.ntaps = 0;
             }
-            if (want_tc && nt > 0 && conv_tc_supported(p)) rc = launch_conv_tc(p, w_tc, kh * kw, s);
-            else rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
+            if (tc_multi) { phases[nph++] = p; continue; }
+            rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
             if (rc != 0) return rc;
         }
+    if (tc_multi && nph > 0) return launch_conv_tc(phases, nph, w_tc, kh * kw, s);   // one launch, blockIdx.y = phase
     return 0;
 }
 

@@ -1,0 +1,180 @@
+// conv_edge.cu -- the two HBM-bound end layers of the hot path (sm_100a, CUDA cores).
+//
+//   conv_in_k4s2:   encoder.py:29-31  Conv2d(3 -> 64, k4 s2 p1) + ReLU, reads the NCHW module
+//                   input, writes NHWC.  K_red = 48: far too thin for a tensor-core tile
+//                   (SURVEY 7.3.4); arithmetic intensity ~20 F/B.
+//   convt_out_k4s2: decoder.py:34-35  ConvTranspose2d(64 -> 3, k4 s2 p1), reads NHWC, writes
+//                   the NCHW module output.  One thread owns one INPUT pixel and produces its
+//                   2x2 output block for every output channel from the 3x3 input
+//                   neighbourhood (the four sub-pixel phases share the loads).
+// Both keep the (tiny) weight tensor in shared memory, read activations through L1 and
+// write fully coalesced rows.  fp32 FFMA arithmetic in every precision mode.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ Conv2d(Cin<=4 -> Cout), k4 s2 p1
+// thread = (output pixel, group of 32 output channels); warp = 32 consecutive pixels of one
+// channel group, so weight reads are warp-wide broadcasts.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_in_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
+                    float *__restrict__ y, int B, int H, int W, int Cout, int relu) {
+    extern __shared__ __align__(16) float wsm[];          // [16*CIN][Cout]
+    const int K = 16 * CIN;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) wsm[i] = __ldg(wp + i);
+    __syncthreads();
+    const int OH = H / 2, OW = W / 2;                      // (H + 2 - 4)/2 + 1
+    const int groups = Cout / 32;
+    const long long npix = (long long)B * OH * OW;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long pix = (gwarp / groups) * 32 + lane;
+    const int cg = (int)(gwarp % groups);
+    if (pix >= npix) return;
+    const int ox = (int)(pix % OW);
+    const long long t = pix / OW;
+    const int oy = (int)(t % OH);
+    const int n = (int)(t / OH);
+
+    float in[16 * CIN];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int iy = 2 * oy - 1 + r, ix = 2 * ox - 1 + s;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                in[(r * 4 + s) * CIN + c] = ok ? __ldg(x + (((long long)n * CIN + c) * H + iy) * W + ix) : 0.f;
+        }
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = bias ? __ldg(bias + cg * 32 + j) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 16 * CIN; ++k) {
+        const float4 *w4 = reinterpret_cast<const float4 *>(wsm + (size_t)k * Cout + cg * 32);
+        const float a = in[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 w = w4[j];
+            acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+        }
+    }
+    float4 *dst = reinterpret_cast<float4 *>(y + pix * Cout + cg * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        dst[j] = o;
+    }
+}
+
+// ------------------------------------------------------------------ ConvTranspose2d(Cin -> Cout<=4), k4 s2 p1
+// out[2j+py][2i+px] = sum over the two kernel rows/cols of matching parity:
+//   py = 0: (kh=1, dy=0), (kh=3, dy=-1)      py = 1: (kh=0, dy=+1), (kh=2, dy=0)     (same in x)
+template <int COUT>
+__global__ void __launch_bounds__(256)
+convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
+                      float *__restrict__ y, int B, int H, int W, int Cin, int relu) {
+    extern __shared__ __align__(16) float wsm[];          // [16 taps][Cin] float4 (co padded to 4)
+    for (int i = threadIdx.x; i < 16 * Cin * 4; i += blockDim.x) {
+        const int co = i & 3, rest = i >> 2;                // rest = tap*Cin + ci
+        wsm[i] = co < COUT ? __ldg(wp + (size_t)rest * COUT + co) : 0.f;
+    }
+    __syncthreads();
+    const long long npix = (long long)B * H * W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int i0 = (int)(pix % W);
+    const long long t = pix / W;
+    const int j0 = (int)(t % H);
+    const int n = (int)(t / H);
+
+    float acc[2][2][COUT];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[a][b][c] = bias ? __ldg(bias + c) : 0.f;
+
+    const float4 *w4 = reinterpret_cast<const float4 *>(wsm);
+    for (int ci = 0; ci < Cin; ci += 4) {
+        float4 xin[3][3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int iy = j0 + dy, ix = i0 + dx;
+                xin[dy + 1][dx + 1] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                    ? __ldg(reinterpret_cast<const float4 *>(x + (((long long)n * H + iy) * W + ix) * Cin + ci))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        // kernel row / input row offset of the a-th tap of output parity py
+                        const int kh = (py == 0) ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
+                        const int dy = (py == 0) ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
+                        const int kw = (px == 0) ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
+                        const int dx = (px == 0) ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0);
+                        const float4 xv = xin[dy + 1][dx + 1];
+                        const float4 *wt = w4 + (size_t)(kh * 4 + kw) * Cin + ci;
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 w = wt[u];
+                            const float wc[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int c = 0; c < COUT; ++c) acc[py][px][c] = fmaf(xs[u], wc[c], acc[py][px][c]);
+                        }
+                    }
+    }
+    const int OH = 2 * H, OW = 2 * W;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c)
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            float2 o = make_float2(acc[py][0][c], acc[py][1][c]);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+            *reinterpret_cast<float2 *>(y + (((long long)n * COUT + c) * OH + 2 * j0 + py) * OW + 2 * i0) = o;
+        }
+}
+
+}  // namespace
+
+// Conv2d(Cin in {1..4} -> Cout % 32 == 0), k4 s2 p1, NCHW in, NHWC out.  wp = FFMA packing.
+int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
+                        int Cout, int relu, cudaStream_t s) {
+    if (Cin != 3 || Cout % 32 != 0 || H % 2 || W % 2) return VQB_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)16 * Cin * Cout * sizeof(float);
+    if (smem > 48 * 1024) return VQB_ERR_UNSUPPORTED;
+    const long long npix = (long long)B * (H / 2) * (W / 2);
+    const long long warps = (npix + 31) / 32 * (Cout / 32);
+    const long long blocks = (warps + 7) / 8;
+    if (blocks > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    conv_in_k4s2_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(x, wp, bias, y, B, H, W, Cout, relu);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}
+
+// ConvTranspose2d(Cin % 4 == 0 -> Cout == 3), k4 s2 p1, NHWC in, NCHW out.  wp = FFMA packing.
+int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
+                          int Cout, int relu, cudaStream_t s) {
+    if (Cout != 3 || Cin % 4 != 0) return VQB_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)16 * Cin * 4 * sizeof(float);
+    if (smem > 48 * 1024) return VQB_ERR_UNSUPPORTED;
+    const long long npix = (long long)B * H * W;
+    const long long blocks = (npix + 255) / 256;
+    if (blocks > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    convt_out_k4s2_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(x, wp, bias, y, B, H, W, Cin, relu);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}

@@ -15,26 +15,29 @@
 //   * W_t,c is a 2-D TMA box {32 ch, Cout} of the tap-major packed weight [t][Cout][Cin].
 //   * warp 0 = TMA producer, warp 1 = tcgen05.mma kind::tf32 issuer (fp32 accumulators
 //     in TMEM), warp 2 = TMEM allocator, warps 4-7 = epilogue: tcgen05.ld -> +bias
-//     -> +skip -> ReLU -> coalesced 16-byte NHWC stores.  3-stage mbarrier ring.
+//     -> +skip -> ReLU -> coalesced 16-byte NHWC stores.  Up to 8-stage mbarrier ring
+//     (the k-loop of one tile is TMA-latency bound, so the ring is as deep as smem allows).
+//   * the sub-pixel phases of a stride-2 transposed conv run in ONE launch (blockIdx.y).
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace {
 
 constexpr int CT_THREADS = 256;
-constexpr int CT_STAGES = 3;
+constexpr int CT_MAX_STAGES = 8;
 constexpr int A_BYTES = 128 * 128;                 // 128 pixels x 32 fp32
 
 struct ConvTcParams {
     const float *bias, *skip;
     float *out;
     int B, Cin, Cout;
-    int OHg, OWg;                                  // output grid of this launch
     int BW, BH, BN;                                // tile = BN images x BH rows x BW cols = 128 pixels
-    int tiles_x, tiles_y;
-    int in_step, out_step, out_py, out_px;
-    int ntaps;
-    int tap_w[VQB_MAX_TAPS], tap_dy[VQB_MAX_TAPS], tap_dx[VQB_MAX_TAPS];
+    int tiles_x, tiles_y;                          // of the largest phase grid
+    int in_step, out_step;
+    int stages;
+    // blockIdx.y = phase (1 for a plain conv, stride^2 sub-pixel phases of a transposed conv)
+    int OHg[4], OWg[4], out_py[4], out_px[4], ntaps[4];
+    int tap_w[4][VQB_MAX_TAPS], tap_dy[4][VQB_MAX_TAPS], tap_dx[4][VQB_MAX_TAPS];
     long long out_sn, out_sh, out_sw;              // NHWC element strides of out / skip
     int relu;
 };
@@ -48,12 +51,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
     unsigned char *sm = smem_raw + (sbase - raw);
     const int b_bytes = p.Cout * 128;
     const int stage_bytes = A_BYTES + b_bytes;
+    const int CT_STAGES = p.stages;
+    const int ph = blockIdx.y;
     const uint32_t bars = sbase + CT_STAGES * stage_bytes;      // full[S], empty[S], tfull
-    float *bias_s = reinterpret_cast<float *>(sm + CT_STAGES * stage_bytes + 64);
-    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + CT_STAGES * stage_bytes + 56);
+    float *bias_s = reinterpret_cast<float *>(sm + CT_STAGES * stage_bytes + 192);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + CT_STAGES * stage_bytes + 176);
     auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (CT_STAGES + s); };
-    const uint32_t tfull = bars + 8u * (2 * CT_STAGES);
+    auto empty = [&](int s) { return bars + 8u * (CT_MAX_STAGES + s); };
+    const uint32_t tfull = bars + 8u * (2 * CT_MAX_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tcols = 32;
@@ -73,27 +78,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
         ptx::fence_mbar_init();
     }
     for (int c = tid; c < p.Cout; c += CT_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-    if (warp == 2) ptx::tmem_alloc(sbase + CT_STAGES * stage_bytes + 56, (uint32_t)tcols);
+    if (warp == 2) ptx::tmem_alloc(sbase + CT_STAGES * stage_bytes + 176, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
     const int kchunks = p.Cin / 32;
-    const int ksteps = p.ntaps * kchunks;
+    const int ksteps = p.ntaps[ph] * kchunks;
 
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < ksteps; ++i) {
                 const int s = i % CT_STAGES;
-                const uint32_t ph = (uint32_t)((i / CT_STAGES) & 1);
+                const uint32_t par = (uint32_t)((i / CT_STAGES) & 1);
                 const int t = i / kchunks, cc = i - t * kchunks;
-                ptx::mbar_wait(empty(s), ph ^ 1);
+                ptx::mbar_wait(empty(s), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
                 const uint32_t dst = sbase + s * stage_bytes;
-                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 * p.in_step + p.tap_dx[t],
-                                 gy0 * p.in_step + p.tap_dy[t], n0);
-                ptx::tma_load_2d(dst + A_BYTES, &tma_w, full(s), cc * 32, p.tap_w[t] * p.Cout);
+                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 * p.in_step + p.tap_dx[ph][t],
+                                 gy0 * p.in_step + p.tap_dy[ph][t], n0);
+                ptx::tma_load_2d(dst + A_BYTES, &tma_w, full(s), cc * 32, p.tap_w[ph][t] * p.Cout);
             }
         }
     } else if (warp == 1) {
@@ -101,8 +106,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
             const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
             for (int i = 0; i < ksteps; ++i) {
                 const int s = i % CT_STAGES;
-                const uint32_t ph = (uint32_t)((i / CT_STAGES) & 1);
-                ptx::mbar_wait(full(s), ph);
+                const uint32_t par = (uint32_t)((i / CT_STAGES) & 1);
+                ptx::mbar_wait(full(s), par);
                 ptx::tc_fence_after();
                 const uint32_t a = sbase + s * stage_bytes, b = a + A_BYTES;
 #pragma unroll
@@ -119,9 +124,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
         const int row = q * 32 + lane;
         const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
         const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
-        const bool valid = gx < p.OWg && gy < p.OHg && n < p.B;
-        const long long ob = (long long)n * p.out_sn + (long long)(gy * p.out_step + p.out_py) * p.out_sh +
-                             (long long)(gx * p.out_step + p.out_px) * p.out_sw;
+        const bool valid = gx < p.OWg[ph] && gy < p.OHg[ph] && n < p.B;
+        const long long ob = (long long)n * p.out_sn + (long long)(gy * p.out_step + p.out_py[ph]) * p.out_sh +
+                             (long long)(gx * p.out_step + p.out_px[ph]) * p.out_sw;
         if (ksteps > 0) {
             ptx::mbar_wait(tfull, 0);
             ptx::tc_fence_after();
@@ -171,25 +176,41 @@ bool conv_tc_supported(const ConvLaunch &p) {
     const bool in_nhwc = p.in_sc == 1 && p.in_sw == p.Cin;
     const bool out_nhwc = p.out_sc == 1 && p.out_sw == p.Cout;
     return in_nhwc && out_nhwc && p.Cin % 32 == 0 && p.Cout % 16 == 0 && p.Cout >= 16 && p.Cout <= 256 &&
-           p.in_step >= 1 && p.in_step <= 2 && p.ntaps >= 1 &&
+           p.in_step >= 1 && p.in_step <= 2 &&
            (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
            (p.skip == nullptr || (reinterpret_cast<uintptr_t>(p.skip) & 15) == 0);
 }
 
-// w_tc: tap-major K-major weight [tap][Cout][Cin] (vqb_pack_conv_weight_f32, second half)
-int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaStream_t s) {
+// ph[0..nph): the phases of ONE layer (same tensors, strides and steps; they differ in the
+// output grid, the sub-pixel offset and the tap list).  w_tc: tap-major K-major weight
+// [tap][Cout][Cin] (vqb_pack_conv_weight_f32, second half).
+int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s) {
+    if (nph < 1 || nph > 4) return VQB_ERR_UNSUPPORTED;
+    const ConvLaunch &p = ph[0];
     ConvTcParams q;
     q.bias = p.bias; q.skip = p.skip; q.out = p.out;
-    q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout; q.OHg = p.OHg; q.OWg = p.OWg;
-    q.BW = pow2_ceil(p.OWg) < 16 ? pow2_ceil(p.OWg) : 16;
-    q.BH = pow2_ceil(p.OHg) < 128 / q.BW ? pow2_ceil(p.OHg) : 128 / q.BW;
+    q.B = p.B; q.Cin = p.Cin; q.Cout = p.Cout;
+    int maxw = 0, maxh = 0;
+    for (int i = 0; i < 4; ++i) {
+        const ConvLaunch &r = ph[i < nph ? i : 0];
+        q.OHg[i] = i < nph ? r.OHg : 0; q.OWg[i] = i < nph ? r.OWg : 0;
+        q.out_py[i] = r.out_py; q.out_px[i] = r.out_px; q.ntaps[i] = i < nph ? r.ntaps : 0;
+        for (int t = 0; t < VQB_MAX_TAPS; ++t) {
+            q.tap_w[i][t] = t < r.ntaps ? r.tap_w[t] : 0;
+            q.tap_dy[i][t] = t < r.ntaps ? r.tap_dy[t] : 0;
+            q.tap_dx[i][t] = t < r.ntaps ? r.tap_dx[t] : 0;
+        }
+        if (q.OWg[i] > maxw) maxw = q.OWg[i];
+        if (q.OHg[i] > maxh) maxh = q.OHg[i];
+    }
+    if (maxw <= 0 || maxh <= 0) return 0;
+    q.BW = pow2_ceil(maxw) < 16 ? pow2_ceil(maxw) : 16;
+    q.BH = pow2_ceil(maxh) < 128 / q.BW ? pow2_ceil(maxh) : 128 / q.BW;
     q.BN = 128 / (q.BW * q.BH);
-    q.tiles_x = (p.OWg + q.BW - 1) / q.BW;
-    q.tiles_y = (p.OHg + q.BH - 1) / q.BH;
+    q.tiles_x = (maxw + q.BW - 1) / q.BW;
+    q.tiles_y = (maxh + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
-    q.in_step = p.in_step; q.out_step = p.out_step; q.out_py = p.out_py; q.out_px = p.out_px;
-    q.ntaps = p.ntaps;
-    for (int t = 0; t < p.ntaps; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
+    q.in_step = p.in_step; q.out_step = p.out_step;
     q.out_sn = p.out_sn; q.out_sh = p.out_sh; q.out_sw = p.out_sw; q.relu = p.relu;
 
     CUtensorMap tin, tw;
@@ -205,7 +226,14 @@ int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaS
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const int stage_bytes = A_BYTES + p.Cout * 128;
-    const int smem = CT_STAGES * stage_bytes + 64 + p.Cout * 4 + 1024;
+    int maxk = 1;
+    for (int i = 0; i < nph; ++i) if (q.ntaps[i] * (p.Cin / 32) > maxk) maxk = q.ntaps[i] * (p.Cin / 32);
+    int stages = (200 * 1024) / stage_bytes;      // deep ring: the k-loop is TMA-latency bound
+    if (stages > CT_MAX_STAGES) stages = CT_MAX_STAGES;
+    if (stages > maxk) stages = maxk;
+    if (stages < 1) stages = 1;
+    q.stages = stages;
+    const int smem = stages * stage_bytes + 192 + p.Cout * 4 + 1024;
     static int attr_max = 0;
     if (smem > attr_max) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -214,7 +242,7 @@ int launch_conv_tc(const ConvLaunch &p, const float *w_tc, int total_taps, cudaS
     }
     const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
     if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
-    conv_tc_kernel<<<(unsigned)grid, CT_THREADS, smem, s>>>(tin, tw, q);
+    conv_tc_kernel<<<dim3((unsigned)grid, (unsigned)nph), CT_THREADS, smem, s>>>(tin, tw, q);
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
