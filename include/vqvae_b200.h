@@ -83,6 +83,19 @@ int vqb_conv2d_f32(const float *in, const float *w_packed, const float *bias,
                    int kh, int kw, int stride, int pad, int transposed, int in_layout,
                    int out_layout, int relu, int precision, void *stream);
 
+/* ---- one ResidualLayer application, residual.py:18-29 -----------------------------
+ * As the reference evaluates it (the in-place ReLU of :19 has already replaced x by
+ * r = relu(x)):   out = act( r + W2 . relu( W1 (*) r ) )
+ * r, out NHWC (B,H,W,C); W1 = res_block.1.weight (Cmid,C,3,3), W2 = res_block.3.weight
+ * (C,Cmid,1,1), both packed by vqb_pack_conv_weight_f32; act = ReLU iff relu_out (inside
+ * a ResidualStack the next consumer always applies ReLU first, residual.py:19,50).
+ * tmp: B*H*W*Cmid floats of scratch (used only by the two-launch FFMA fallback).
+ * With precision != VQB_FP32 and C % 32 == Cmid % 32 == 0 this is ONE tcgen05 kernel
+ * (two chained GEMMs, the Cmid-channel intermediate never leaves the SM).            */
+int vqb_residual_layer_f32(const float *r, const float *w1_packed, const float *w2_packed,
+                           float *out, float *tmp, int B, int H, int W, int C, int Cmid,
+                           int relu_out, int precision, void *stream);
+
 /* ---- VectorQuantizer.forward, quantizer.py:45-76 --------------------------------
  * z        (N, D) fp32 pixel rows (= z.permute(0,2,3,1).view(-1, e_dim), :45-46)
  * codebook (K, D) fp32 embedding.weight (:26)

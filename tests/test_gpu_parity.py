@@ -302,3 +302,23 @@ def test_full_size_properties_cfg2():
     o = cref.vqvae_forward(x[:4].cpu().numpy(), sd, 2)
     np.testing.assert_allclose(x_hat[:4].cpu().numpy(), o["x_hat"], atol=CONV_ATOL, rtol=0)
     assert np.array_equal(idx.view(256, 64)[:4].reshape(-1, 1).cpu().numpy(), o["idx"])
+
+
+@pytest.mark.parametrize("B,H,W,C,Cmid,relu_out", [(2, 8, 8, 128, 32, True), (3, 5, 7, 64, 32, False),
+                                                   (1, 20, 36, 128, 64, True), (5, 4, 4, 32, 32, True)])
+def test_fused_residual_layer_tc_vs_oracle(B, H, W, C, Cmid, relu_out):
+    """res_tc.cu (one tcgen05 kernel, two chained GEMMs) vs residual.py:18-29 semantics."""
+    from vqvae_b200 import ops
+    from vqvae_b200._lib import FP32, TF32
+    rng = np.random.RandomState(B * 1000 + H * 100 + C)
+    r = np.maximum(rng.standard_normal((B, C, H, W)).astype(np.float32), 0)       # r = relu(x)
+    w1 = (rng.standard_normal((Cmid, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32)
+    w2 = (rng.standard_normal((C, Cmid, 1, 1)) / np.sqrt(Cmid)).astype(np.float32)
+    ref = r + cref.conv2d(np.maximum(cref.conv2d(r, w1, None, 1, 1), 0), w2, None, 1, 0)
+    if relu_out:
+        ref = np.maximum(ref, 0)
+    rn = _cuda(np.ascontiguousarray(r.transpose(0, 2, 3, 1)))
+    p1, p2 = ops.pack_conv_weight(_cuda(w1), False), ops.pack_conv_weight(_cuda(w2), False)
+    for prec, atol in ((FP32, 1e-5), (TF32, 6e-3)):
+        y = ops.residual_layer(rn, p1, p2, B=B, H=H, W=W, C=C, Cmid=Cmid, relu_out=relu_out, precision=prec)
+        np.testing.assert_allclose(y.cpu().numpy().transpose(0, 3, 1, 2), ref, atol=atol, rtol=2e-3)

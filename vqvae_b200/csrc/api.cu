@@ -14,6 +14,9 @@ int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, floa
                         int Cout, int relu, cudaStream_t s);
 int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
                           int Cout, int relu, cudaStream_t s);
+bool res_tc_supported(int C, int Cmid, const void *r, const void *out);
+int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
+                  int Cmid, int relu_out, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
 int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
 
@@ -185,4 +188,21 @@ extern "C" int vqb_debug_vq_scores_f32(const float *z, const float *codebook, in
     if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
     return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores,
                         (cudaStream_t)stream);
+}
+
+extern "C" int vqb_residual_layer_f32(const float *r, const float *w1_packed, const float *w2_packed, float *out,
+                                      float *tmp, int B, int H, int W, int C, int Cmid, int relu_out, int precision,
+                                      void *stream) {
+    if (!r || !w1_packed || !w2_packed || !out || !tmp) return VQB_ERR_BAD_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cmid <= 0) return VQB_ERR_BAD_ARG;
+    if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
+    if (precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out))
+        return launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C, Cmid,
+                             relu_out, (cudaStream_t)stream);
+    // two launches through the generic path (residual.py:20-24 then :23-24,:28)
+    int rc = vqb_conv2d_f32(r, w1_packed, nullptr, nullptr, tmp, B, C, H, W, Cmid, 3, 3, 1, 1, 0, VQB_NHWC, VQB_NHWC, 1,
+                            precision, stream);
+    if (rc) return rc;
+    return vqb_conv2d_f32(tmp, w2_packed, nullptr, r, out, B, Cmid, H, W, C, 1, 1, 1, 0, 0, VQB_NHWC, VQB_NHWC,
+                          relu_out, precision, stream);
 }

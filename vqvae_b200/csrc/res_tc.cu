@@ -1,0 +1,246 @@
+// res_tc.cu -- one ResidualLayer application as ONE tcgen05 kernel (sm_100a, TF32 operands).
+//
+// Replaces residual.py:18-29 as it is actually evaluated (the in-place ReLU makes the
+// layer relu(x) + W2 . relu(W1 (*) relu(x)); the caller passes r = relu(x) >= 0):
+//     out = act( r + W2 . relu( W1 (*) r ) )          W1: 3x3 C->Cmid (no bias), W2: 1x1 Cmid->C
+// with act = ReLU when the next consumer applies one first (always inside a ResidualStack).
+// Five PyTorch launches (relu, conv, relu, conv, add) and the (B,Cmid,H,W) intermediate's HBM
+// round trip become two chained GEMMs inside one CTA per 128-pixel tile:
+//   GEMM1  D1[128][Cmid] = sum_{9 taps, C/32 chunks} A[128][32] * W1[Cmid][32]^T   (TMA ring, as conv_tc.cu)
+//   epi1   tcgen05.ld D1 -> ReLU -> written back to shared memory as the K-major, 128B-swizzled
+//          A operand of GEMM2 (one 128-byte row per pixel per 32 channels)
+//   GEMM2  D2[128][C] = A2[128][Cmid] * W2[C][Cmid]^T
+//   epi2   tcgen05.ld D2 -> + r (skip, from global/L2) -> ReLU -> NHWC store
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_MAX_STAGES = 8;
+constexpr int RT_A_BYTES = 128 * 128;
+
+struct ResTcParams {
+    const float *skip;      // r, NHWC (B,H,W,C)
+    float *out;             // NHWC (B,H,W,C)
+    int B, H, W, C, Cmid;
+    int BW, BH, BN, tiles_x, tiles_y;
+    int stages;
+    int relu_out;
+};
+
+__global__ void __launch_bounds__(RT_THREADS)
+res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w1,
+              const __grid_constant__ CUtensorMap tma_w2, const ResTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+
+    const int S = p.stages;
+    const int b1_bytes = p.Cmid * 128;
+    const int stage_bytes = RT_A_BYTES + b1_bytes;
+    const int matoms = p.Cmid / 32;                         // 128-byte atoms of the GEMM2 K dimension
+    const uint32_t a2_off = (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
+    const uint32_t w2_off = a2_off + (uint32_t)(matoms * RT_A_BYTES);   // W2: matoms x [C rows][128 B]
+    const uint32_t bar_off = w2_off + (uint32_t)(matoms * p.C * 128);
+    const uint32_t bars = sbase + bar_off;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (RT_MAX_STAGES + s); };
+    const uint32_t w2full = bars + 8u * (2 * RT_MAX_STAGES + 0);
+    const uint32_t d1full = bars + 8u * (2 * RT_MAX_STAGES + 1);
+    const uint32_t a2ready = bars + 8u * (2 * RT_MAX_STAGES + 2);
+    const uint32_t d2full = bars + 8u * (2 * RT_MAX_STAGES + 3);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * RT_MAX_STAGES + 4));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int tcols = 32;
+    while (tcols < p.Cmid + p.C) tcols <<= 1;
+    const uint32_t d2col = (uint32_t)p.Cmid;                // D1 at column 0, D2 right after it
+
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int gx0 = tx * p.BW, gy0 = ty * p.BH, n0 = tile * p.BN;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tma_in);
+        ptx::prefetch_tmap(&tma_w1);
+        ptx::prefetch_tmap(&tma_w2);
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+        ptx::mbar_init(w2full, 1);
+        ptx::mbar_init(d1full, 1);
+        ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
+        ptx::mbar_init(d2full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * RT_MAX_STAGES + 4), (uint32_t)tcols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int kchunks = p.C / 32;
+    const int ksteps = 9 * kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // W2 (all of it) once
+            ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));
+            for (int a = 0; a < matoms; ++a)
+                ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % S;
+                const uint32_t par = (uint32_t)((i / S) & 1);
+                const int t = i / kchunks, cc = i - t * kchunks;
+                const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
+                ptx::mbar_wait(empty(s), par ^ 1);
+                ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
+                const uint32_t dst = sbase + s * stage_bytes;
+                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 + dx, gy0 + dy, n0);
+                ptx::tma_load_2d(dst + RT_A_BYTES, &tma_w1, full(s), cc * 32, t * p.Cmid);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cmid);
+            const uint32_t idesc2 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.C);
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % S;
+                const uint32_t par = (uint32_t)((i / S) & 1);
+                ptx::mbar_wait(full(s), par);
+                ptx::tc_fence_after();
+                const uint32_t a = sbase + s * stage_bytes, b = a + RT_A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128(a + kk * 32), ptx::smem_desc_sw128(b + kk * 32),
+                                  idesc1, (i > 0 || kk > 0) ? 1u : 0u);
+                ptx::tc_commit(empty(s));
+            }
+            ptx::tc_commit(d1full);
+            // GEMM2 once the epilogue has written relu(D1) as the A2 operand
+            ptx::mbar_wait(w2full, 0);
+            ptx::mbar_wait(a2ready, 0);
+            ptx::tc_fence_after();
+            for (int a = 0; a < matoms; ++a)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
+                                  ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
+                                  (a > 0 || kk > 0) ? 1u : 0u);
+            ptx::tc_commit(d2full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // ---- epilogue 1: relu(D1) -> A2 operand in shared memory ----
+        ptx::mbar_wait(d1full, 0);
+        ptx::tc_fence_after();
+        for (int a = 0; a < matoms; ++a) {
+            float v[32];
+            ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
+            ptx::tmem_ld_wait32(v);
+            unsigned char *arow = sm + a2_off + a * RT_A_BYTES + row * 128;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+                const float4 o = make_float4(fmaxf(v[c16 * 4 + 0], 0.f), fmaxf(v[c16 * 4 + 1], 0.f),
+                                             fmaxf(v[c16 * 4 + 2], 0.f), fmaxf(v[c16 * 4 + 3], 0.f));
+                *reinterpret_cast<float4 *>(arow + ((c16 ^ (row & 7)) << 4)) = o;
+            }
+        }
+        ptx::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core's async proxy
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a2ready);
+
+        // ---- epilogue 2: D2 + skip -> ReLU -> NHWC store ----
+        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+        const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
+        const bool valid = gx < p.W && gy < p.H && n < p.B;
+        const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.C;
+        ptx::mbar_wait(d2full, 0);
+        ptx::tc_fence_after();
+        for (int c0 = 0; c0 < p.C; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
+            ptx::tmem_ld_wait32(v);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
+                    float4 o = make_float4(v[i] + sk.x, v[i + 1] + sk.y, v[i + 2] + sk.z, v[i + 3] + sk.w);
+                    if (p.relu_out) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+}
+
+int rt_pow2_ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+bool res_tc_supported(int C, int Cmid, const void *r, const void *out) {
+    return C % 32 == 0 && C >= 32 && C <= 256 && Cmid % 32 == 0 && Cmid >= 32 && Cmid <= 128 &&
+           (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+// w1_tc: [9][Cmid][C], w2_tc: [1][C][Cmid]  (the K-major halves of vqb_pack_conv_weight_f32)
+int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
+                  int Cmid, int relu_out, cudaStream_t s) {
+    if (!res_tc_supported(C, Cmid, r, out)) return VQB_ERR_UNSUPPORTED;
+    ResTcParams q;
+    q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
+    q.BW = rt_pow2_ceil(W) < 16 ? rt_pow2_ceil(W) : 16;
+    q.BH = rt_pow2_ceil(H) < 128 / q.BW ? rt_pow2_ceil(H) : 128 / q.BW;
+    q.BN = 128 / (q.BW * q.BH);
+    q.tiles_x = (W + q.BW - 1) / q.BW;
+    q.tiles_y = (H + q.BH - 1) / q.BH;
+    const int tiles_n = (B + q.BN - 1) / q.BN;
+
+    CUtensorMap tin, tw1, tw2;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t box[4] = {32u, (uint32_t)q.BW, (uint32_t)q.BH, (uint32_t)q.BN};
+    const uint32_t es[4] = {1u, 1u, 1u, 1u};
+    int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, r, dims, strides, box, es,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, w1_tc, (uint64_t)C, (uint64_t)9 * Cmid,
+                            (uint64_t)C * 4, 32, (uint32_t)Cmid, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tw2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, w2_tc, (uint64_t)Cmid, (uint64_t)C,
+                            (uint64_t)Cmid * 4, 32, (uint32_t)C, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+
+    const int stage_bytes = RT_A_BYTES + Cmid * 128;
+    const int fixed = (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 + 8 * (2 * RT_MAX_STAGES + 4) + 16 + 1024;
+    int stages = (220 * 1024 - fixed) / stage_bytes;
+    if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
+    if (stages > 9 * (C / 32)) stages = 9 * (C / 32);
+    if (stages < 2) return VQB_ERR_UNSUPPORTED;
+    q.stages = stages;
+    const int smem = stages * stage_bytes + fixed;
+    static int attr_max = 0;
+    if (smem > attr_max) {
+        cudaError_t e = cudaFuncSetAttribute(res_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_max = smem;
+    }
+    const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
+    if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    res_tc_kernel<<<(unsigned)grid, RT_THREADS, smem, s>>>(tin, tw1, tw2, q);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}

@@ -116,8 +116,10 @@ class ResidualLayer(nn.Module):
     def _apply_nhwc(self, r, B, H, W, relu_out):
         """r = relu(x) in NHWC.  Returns r + W2.relu(W1 (*) r), optionally ReLU'd
         (the next consumer always applies ReLU first, residual.py:19,50)."""
-        h = _run_conv(self.res_block[1], r, B, H, W, relu=True)
-        return _run_conv(self.res_block[3], h, B, H, W, relu=relu_out, skip=r)
+        c1, c2 = self.res_block[1], self.res_block[3]
+        return ops.residual_layer(r, _PACKED.get(c1.weight, False), _PACKED.get(c2.weight, False), B=B, H=H, W=W,
+                                  C=c1.in_channels, Cmid=c1.out_channels, relu_out=relu_out,
+                                  precision=PRECISIONS[get_precision()])
 
     def forward(self, x):
         xin = x

@@ -97,6 +97,19 @@ def conv2d(x, w_packed, bias, *, B, Cin, H, W, Cout, kh, kw, stride, pad, transp
     return out
 
 
+def residual_layer(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, relu_out, precision=FP32):
+    """out = act(r + W2.relu(W1 (*) r)) on NHWC buffers (vqb_residual_layer_f32)."""
+    _require_cuda(r, "input")
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=r.device)
+    tmp = torch.empty((B, H, W, Cmid), dtype=torch.float32, device=r.device)
+    span = _Span(f"res {C}->{Cmid}->{C} {H}x{W}")
+    check(lib().vqb_residual_layer_f32(r.data_ptr(), w1_packed.data_ptr(), w2_packed.data_ptr(), out.data_ptr(),
+                                       tmp.data_ptr(), B, H, W, C, Cmid, int(bool(relu_out)), precision,
+                                       _stream()), "residual_layer")
+    span.done()
+    return out
+
+
 def vq_forward(z_rows, codebook):
     """Fused VectorQuantizer core on (N,D) rows -> (idx int64 (N,), zq (N,D), sse f64 (1,),
     hist int32 (K,))."""
