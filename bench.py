@@ -370,8 +370,17 @@ def kernel_roofline(top, B, S, K, D, peaks, precision):
         ach = byts / (ms * 1e-3) / 1e9
         return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
-    # conv label: "conv[T] Cin->Cout k{k}s{s} HxW[ +skip]"
     parts = label.split()
+    if parts[0] == "res":                       # "res C->Cmid->C HxW": 3x3 C->Cmid then 1x1 Cmid->C
+        c, cm, _ = (int(v) for v in parts[1].split("->"))
+        h, w = (int(v) for v in parts[2].split("x"))
+        flops = 2.0 * B * h * w * (9 * c * cm + cm * c)
+        tensor_peak = peaks["bf16"] * (1.0 if precision == "bf16" else 0.5)
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"],
+                "note": "tf32/fp32 layers are held against half the measured bf16 cuBLAS peak"}
+    # conv label: "conv[T] Cin->Cout k{k}s{s} HxW[ +skip]"
     transposed = parts[0] == "convT"
     cin, cout = (int(v) for v in parts[1].split("->"))
     k = int(parts[2][1:parts[2].index("s")])

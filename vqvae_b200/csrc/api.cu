@@ -88,8 +88,8 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
         if (!transposed && Cin == 3 && Cout % 32 == 0 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
             H % 2 == 0 && W % 2 == 0 && (size_t)16 * Cin * Cout * 4 <= 48 * 1024)
             return launch_conv_in_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
-        if (transposed && Cout == 3 && Cin % 4 == 0 && in_layout == VQB_NHWC && out_layout == VQB_NCHW &&
-            (size_t)16 * Cin * 16 <= 48 * 1024)
+        if (transposed && Cout == 3 && Cin % 4 == 0 && Cin <= 128 && ((Cin / 4) & (Cin / 4 - 1)) == 0 &&
+            in_layout == VQB_NHWC && out_layout == VQB_NCHW)
             return launch_convt_out_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
     }
 

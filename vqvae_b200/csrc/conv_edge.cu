@@ -17,7 +17,7 @@ namespace {
 // thread = (output pixel, group of 32 output channels); warp = 32 consecutive pixels of one
 // channel group, so weight reads are warp-wide broadcasts.
 template <int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_in_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
                     float *__restrict__ y, int B, int H, int W, int Cout, int relu) {
     extern __shared__ __align__(16) float wsm[];          // [16*CIN][Cout]
@@ -37,29 +37,32 @@ conv_in_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, c
     const int oy = (int)(t % OH);
     const int n = (int)(t / OH);
 
-    float in[16 * CIN];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int iy = 2 * oy - 1 + r, ix = 2 * ox - 1 + s;
-            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-#pragma unroll
-            for (int c = 0; c < CIN; ++c)
-                in[(r * 4 + s) * CIN + c] = ok ? __ldg(x + (((long long)n * CIN + c) * H + iy) * W + ix) : 0.f;
-        }
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = bias ? __ldg(bias + cg * 32 + j) : 0.f;
+    // one kernel row per iteration: 4*CIN inputs in registers, body small enough for the I-cache
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        const int iy = 2 * oy - 1 + r;
+        float in[4 * CIN];
 #pragma unroll
-    for (int k = 0; k < 16 * CIN; ++k) {
-        const float4 *w4 = reinterpret_cast<const float4 *>(wsm + (size_t)k * Cout + cg * 32);
-        const float a = in[k];
+        for (int s = 0; s < 4; ++s) {
+            const int ix = 2 * ox - 1 + s;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 w = w4[j];
-            acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+            for (int c = 0; c < CIN; ++c)
+                in[s * CIN + c] = ok ? __ldg(x + (((long long)n * CIN + c) * H + iy) * W + ix) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4 * CIN; ++k) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(wsm + (size_t)(r * 4 * CIN + k) * Cout + cg * 32);
+            const float a = in[k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = w4[j];
+                acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+            }
         }
     }
     float4 *dst = reinterpret_cast<float4 *>(y + pix * Cout + cg * 32);
@@ -74,34 +77,44 @@ conv_in_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, c
 // ------------------------------------------------------------------ ConvTranspose2d(Cin -> Cout<=4), k4 s2 p1
 // out[2j+py][2i+px] = sum over the two kernel rows/cols of matching parity:
 //   py = 0: (kh=1, dy=0), (kh=3, dy=-1)      py = 1: (kh=0, dy=+1), (kh=2, dy=0)     (same in x)
+// A group of L = Cin/4 lanes owns one input pixel: lane c reads channels 4c..4c+3 of the nine
+// neighbours (one fully coalesced Cin*4-byte row per neighbour and group), accumulates its
+// share of the 2x2xCOUT output block, and the group reduces with shuffles.  Persistent CTAs:
+// the 16*COUT*Cin weights are staged in shared memory once per CTA.
 template <int COUT>
 __global__ void __launch_bounds__(256)
 convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
                       float *__restrict__ y, int B, int H, int W, int Cin, int relu) {
-    extern __shared__ __align__(16) float wsm[];          // [16 taps][Cin] float4 (co padded to 4)
-    for (int i = threadIdx.x; i < 16 * Cin * 4; i += blockDim.x) {
-        const int co = i & 3, rest = i >> 2;                // rest = tap*Cin + ci
-        wsm[i] = co < COUT ? __ldg(wp + (size_t)rest * COUT + co) : 0.f;
+    extern __shared__ __align__(16) float wsm[];          // [16 taps][COUT][Cin]
+    for (int i = threadIdx.x; i < 16 * COUT * Cin; i += blockDim.x) {
+        const int ci = i % Cin, rest = i / Cin;            // rest = tap*COUT + co
+        const int co = rest % COUT, tap = rest / COUT;
+        wsm[i] = __ldg(wp + ((size_t)tap * Cin + ci) * COUT + co);
     }
     __syncthreads();
+    const int L = Cin / 4;                                 // lanes per pixel (power of two <= 32)
+    const int per_warp = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const int c4 = (lane % L) * 4, sub = lane / L;
     const long long npix = (long long)B * H * W;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const int i0 = (int)(pix % W);
-    const long long t = pix / W;
-    const int j0 = (int)(t % H);
-    const int n = (int)(t / H);
-
-    float acc[2][2][COUT];
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int OH = 2 * H, OW = 2 * W;
+    for (long long base = gwarp * per_warp; base < npix; base += warps_total * per_warp) {
+        const long long pix = base + sub;
+        const bool live = pix < npix;
+        const long long pp = live ? pix : npix - 1;
+        const int i0 = (int)(pp % W);
+        const long long t = pp / W;
+        const int j0 = (int)(t % H);
+        const int n = (int)(t / H);
+        float acc[2][2][COUT];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+            for (int b = 0; b < 2; ++b)
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[a][b][c] = bias ? __ldg(bias + c) : 0.f;
-
-    const float4 *w4 = reinterpret_cast<const float4 *>(wsm);
-    for (int ci = 0; ci < Cin; ci += 4) {
+                for (int c = 0; c < COUT; ++c) acc[a][b][c] = 0.f;
         float4 xin[3][3];
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
@@ -109,7 +122,7 @@ convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp,
             for (int dx = -1; dx <= 1; ++dx) {
                 const int iy = j0 + dy, ix = i0 + dx;
                 xin[dy + 1][dx + 1] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                    ? __ldg(reinterpret_cast<const float4 *>(x + (((long long)n * H + iy) * W + ix) * Cin + ci))
+                    ? __ldg(reinterpret_cast<const float4 *>(x + (((long long)n * H + iy) * W + ix) * Cin + c4))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
@@ -120,32 +133,45 @@ convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp,
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
-                        // kernel row / input row offset of the a-th tap of output parity py
                         const int kh = (py == 0) ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
                         const int dy = (py == 0) ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
                         const int kw = (px == 0) ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
                         const int dx = (px == 0) ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0);
                         const float4 xv = xin[dy + 1][dx + 1];
-                        const float4 *wt = w4 + (size_t)(kh * 4 + kw) * Cin + ci;
-                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float4 w = wt[u];
-                            const float wc[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                            for (int c = 0; c < COUT; ++c) acc[py][px][c] = fmaf(xs[u], wc[c], acc[py][px][c]);
+                        for (int c = 0; c < COUT; ++c) {
+                            const float4 w = *reinterpret_cast<const float4 *>(
+                                wsm + ((size_t)(kh * 4 + kw) * COUT + c) * Cin + c4);
+                            acc[py][px][c] = fmaf(xv.x, w.x, acc[py][px][c]);
+                            acc[py][px][c] = fmaf(xv.y, w.y, acc[py][px][c]);
+                            acc[py][px][c] = fmaf(xv.z, w.z, acc[py][px][c]);
+                            acc[py][px][c] = fmaf(xv.w, w.w, acc[py][px][c]);
                         }
                     }
-    }
-    const int OH = 2 * H, OW = 2 * W;
+        // reduce over the L lanes of the pixel (butterfly: every lane ends with the total)
 #pragma unroll
-    for (int c = 0; c < COUT; ++c)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int py = 0; py < 2; ++py) {
-            float2 o = make_float2(acc[py][0][c], acc[py][1][c]);
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-            *reinterpret_cast<float2 *>(y + (((long long)n * COUT + c) * OH + 2 * j0 + py) * OW + 2 * i0) = o;
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    float v = acc[a][b][c];
+                    for (int off = L >> 1; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    acc[a][b][c] = v;
+                }
+        if (live && (lane % L) == 0) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                const float bv = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    float2 o = make_float2(acc[py][0][c] + bv, acc[py][1][c] + bv);
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                    *reinterpret_cast<float2 *>(y + (((long long)n * COUT + c) * OH + 2 * j0 + py) * OW + 2 * i0) = o;
+                }
+            }
         }
+    }
 }
 
 }  // namespace
@@ -168,12 +194,18 @@ int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, floa
 // ConvTranspose2d(Cin % 4 == 0 -> Cout == 3), k4 s2 p1, NHWC in, NCHW out.  wp = FFMA packing.
 int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
                           int Cout, int relu, cudaStream_t s) {
-    if (Cout != 3 || Cin % 4 != 0) return VQB_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)16 * Cin * 4 * sizeof(float);
+    const int L = Cin / 4;
+    if (Cout != 3 || Cin % 4 != 0 || L < 1 || L > 32 || (L & (L - 1)) != 0) return VQB_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)16 * Cout * Cin * sizeof(float);
     if (smem > 48 * 1024) return VQB_ERR_UNSUPPORTED;
     const long long npix = (long long)B * H * W;
-    const long long blocks = (npix + 255) / 256;
-    if (blocks > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    const long long warps = (npix + (32 / L) - 1) / (32 / L);
+    long long blocks = (warps + 7) / 8;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;       // persistent: weights staged once per CTA
+    if (blocks < 1) blocks = 1;
     convt_out_k4s2_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(x, wp, bias, y, B, H, W, Cin, relu);
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
