@@ -1,0 +1,115 @@
+"""CPU-only checks of the C-ABI boundary and of the drop-in nn.Module API (no compute:
+there is no GPU here and the product has no CPU fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "vqvae_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vqb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from vqvae_b200.build import build
+    lib = ctypes.CDLL(build())
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vqvae_b200.h but not exported"
+    lib.vqb_abi_version.restype = ctypes.c_int
+    assert lib.vqb_abi_version() == 1
+    lib.vqb_error_string.restype = ctypes.c_char_p
+    assert b"workspace" in lib.vqb_error_string(-3)
+
+
+def test_ctypes_signature_table_matches_header():
+    from vqvae_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _header_functions()
+
+
+def test_argument_validation_without_a_gpu():
+    """Bad arguments are rejected before any CUDA call (safe on a CPU box)."""
+    from vqvae_b200 import _lib
+    lib = _lib.lib()
+    assert lib.vqb_conv2d_f32(None, None, None, None, None, 1, 3, 8, 8, 4, 3, 3, 1, 1, 0, 0, 0, 0, 0, None) == -1
+    assert lib.vqb_vq_forward_f32(None, None, 1, 1, 4, None, None, None, None, None, 0, None) == -1
+    assert lib.vqb_set_vq_kernel(7) == -1
+    assert lib.vqb_vq_workspace_bytes(1024, 512, 64) > 0
+
+
+def test_reference_constructor_signatures_and_import_paths():
+    from models.vqvae import VQVAE
+    from models.encoder import Encoder
+    from models.decoder import Decoder
+    from models.quantizer import VectorQuantizer
+    from models.residual import ResidualLayer, ResidualStack
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]   # noqa: E731
+    assert sig(VQVAE) == ["h_dim", "res_h_dim", "n_res_layers", "n_embeddings", "embedding_dim", "beta",
+                          "save_img_embedding_map"]                       # vqvae.py:11-12
+    assert sig(Encoder) == ["in_dim", "h_dim", "n_res_layers", "res_h_dim"]   # encoder.py:24
+    assert sig(Decoder) == ["in_dim", "h_dim", "n_res_layers", "res_h_dim"]   # decoder.py:22
+    assert sig(VectorQuantizer) == ["n_e", "e_dim", "beta"]                   # quantizer.py:20
+    assert sig(ResidualLayer) == ["in_dim", "h_dim", "res_h_dim"]             # residual.py:16
+    assert sig(ResidualStack) == ["in_dim", "h_dim", "res_h_dim", "n_res_layers"]   # residual.py:41
+    assert list(inspect.signature(VQVAE.forward).parameters) == ["self", "x", "verbose"]
+
+
+def test_state_dict_keys_shapes_and_shared_residual_weights():
+    from models.vqvae import VQVAE
+    from oracle.weights import state_dict_shapes
+    m = VQVAE(128, 32, 2, 512, 64, 0.25)
+    sd = m.state_dict()
+    want = state_dict_shapes(128, 32, 2, 512, 64)
+    assert list(sd.keys()) == [k for k, _, _ in want]            # 23 keys, reference order
+    for k, shape, _ in want:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sum(v.numel() for v in sd.values()) == 694851          # duplicated stack.1.* keys included
+    assert sum(p.numel() for p in m.parameters()) == 612931       # unique parameters (Q1)
+    st = m.encoder.conv_stack[5].stack
+    assert st[0] is st[1]
+    assert sd["encoder.conv_stack.5.stack.0.res_block.1.weight"].data_ptr() == \
+        sd["encoder.conv_stack.5.stack.1.res_block.1.weight"].data_ptr()
+    # load_state_dict accepts the duplicated keys; attributes callers touch exist
+    m.load_state_dict({k: v.clone() for k, v in sd.items()})
+    assert m.img_to_embedding_map is None and m.vector_quantization.n_e == 512
+    assert VQVAE(32, 8, 1, 16, 8, 0.25, save_img_embedding_map=True).img_to_embedding_map == {i: [] for i in range(16)}
+    w = m.vector_quantization.embedding.weight
+    assert float(w.abs().max()) <= 1.0 / 512 + 1e-9               # quantizer.py:27 init
+
+
+def test_same_seed_gives_reference_init_order():
+    """Parameter creation order equals the reference's, so the same torch seed gives the same
+    weights; pinned by a fingerprint taken from the unmodified reference (tests/golden)."""
+    import json
+    from models.vqvae import VQVAE
+    fp = json.load(open(os.path.join(ROOT, "tests", "golden", "init_fingerprint.json")))
+    torch.manual_seed(fp["seed"])
+    m = VQVAE(*fp["args"])
+    for k, v in m.state_dict().items():
+        assert abs(float(v.double().sum()) - fp["sums"][k]) <= 1e-9 + 1e-12 * abs(fp["sums"][k]), k
+
+
+def test_no_cpu_fallback():
+    from models.vqvae import VQVAE
+    m = VQVAE(32, 8, 1, 16, 8, 0.25)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError):
+        m.encoder(torch.zeros(1, 3, 8, 8))
+
+
+def test_product_never_imports_the_oracle():
+    for d in ("vqvae_b200", "models"):
+        for root, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(root, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(root, f)

@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .dist import reduce_vq_stats
 from ._lib import NCHW, NHWC, PRECISIONS
 
 _PRECISION = {"value": "fp32"}
@@ -252,13 +253,9 @@ class VectorQuantizer(nn.Module):
         if group is not None and torch.distributed.get_world_size(group) > 1:
             # batch-sharded forward: loss and perplexity are the only
             # cross-sample quantities; reduce their sufficient statistics.
-            # One tiny all-reduce of [hist (K) | sse] as float64 (counts are exact in
-            # f64).  Shards are equal-sized (contiguous batch split), so the global row
-            # count is n_local * world_size and no host sync is needed.
-            stats = torch.cat([hist.double(), sse])
-            torch.distributed.all_reduce(stats, group=group)
-            hist = stats[:-1].round().to(torch.int32)
-            sse = stats[-1:].contiguous()
+            # one tiny all-reduce of [hist (K) | sse]; shards are equal-sized (contiguous batch
+            # split), so the global row count is n_local * world_size: no host sync needed
+            hist, sse = reduce_vq_stats(hist, sse, group)
             n_total = n_total * torch.distributed.get_world_size(group)
         loss, perp = ops.vq_finish(sse, hist, n_total, self.n_e, self.e_dim, self.beta)
         return loss, zq, perp, idx
