@@ -17,6 +17,8 @@ int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, fl
 bool res_tc_supported(int C, int Cmid, const void *r, const void *out);
 int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
                   int Cmid, int relu_out, cudaStream_t s);
+bool conv_halo_supported(const ConvLaunch &p);
+int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
 int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
 
@@ -114,6 +116,7 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 p.tap_dy[t] = transposed ? pad - r : r - pad;
                 p.tap_dx[t] = transposed ? pad - c : c - pad;
             }
+        if (want_tc && conv_halo_supported(p)) return launch_conv_halo(p, w_tc, s);
         if (want_tc && conv_tc_supported(p)) return launch_conv_tc(&p, 1, w_tc, kh * kw, s);
         return small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
     }

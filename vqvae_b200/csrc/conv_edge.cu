@@ -82,15 +82,12 @@ conv_in_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, c
 // share of the 2x2xCOUT output block, and the group reduces with shuffles.  Persistent CTAs:
 // the 16*COUT*Cin weights are staged in shared memory once per CTA.
 template <int COUT>
-__global__ void __launch_bounds__(256)
-convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
+__global__ void __launch_bounds__(256, 2)
+convt_out_k4s2_kernel(const float *__restrict__ x, const float *__restrict__ wk, const float *__restrict__ bias,
                       float *__restrict__ y, int B, int H, int W, int Cin, int relu) {
-    extern __shared__ __align__(16) float wsm[];          // [16 taps][COUT][Cin]
-    for (int i = threadIdx.x; i < 16 * COUT * Cin; i += blockDim.x) {
-        const int ci = i % Cin, rest = i / Cin;            // rest = tap*COUT + co
-        const int co = rest % COUT, tap = rest / COUT;
-        wsm[i] = __ldg(wp + ((size_t)tap * Cin + ci) * COUT + co);
-    }
+    extern __shared__ __align__(16) float wsm[];          // [16 taps][COUT][Cin] = the K-major packing
+    for (int i = threadIdx.x; i < 16 * COUT * Cin / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(wsm)[i] = __ldg(reinterpret_cast<const float4 *>(wk) + i);
     __syncthreads();
     const int L = Cin / 4;                                 // lanes per pixel (power of two <= 32)
     const int per_warp = 32 / L;
@@ -204,9 +201,11 @@ int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, fl
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;       // persistent: weights staged once per CTA
+    if (blocks > (long long)sms * 2) blocks = (long long)sms * 2;       // persistent: weights staged once per CTA
     if (blocks < 1) blocks = 1;
-    convt_out_k4s2_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(x, wp, bias, y, B, H, W, Cin, relu);
+    // K-major half of the packed weight: [tap][Cout][Cin]
+    convt_out_k4s2_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(x, wp + (size_t)16 * Cin * Cout, bias, y, B, H, W,
+                                                                 Cin, relu);
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

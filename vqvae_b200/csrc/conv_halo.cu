@@ -1,0 +1,239 @@
+// conv_halo.cu -- tcgen05 implicit GEMM for 3x3 / stride-1 / pad-1 layers with A-operand reuse.
+//
+// conv_tc.cu fetches the 128-pixel A tile once per tap (9x for a 3x3), which makes the k-loop
+// L2->SM feed bound (profiles/r01: tensor pipe 7-30 % active).  Here the input tile is loaded
+// ONCE per 32-channel chunk, with its 1-pixel halo, as a TMA box {32 ch, 16 px, BN img, BH+2 rows}
+// (tensor-map dims ordered c,w,n,h so the rows of the BN images interleave), and the nine taps are
+// nine UMMA shared-memory descriptors into that one tile: tap (dy,dx) starts (dy+1)*BN*16+(dx+1)
+// 128-byte rows further in, 8-pixel row groups stay 16 rows (2048 B) apart, and because the
+// padded row length is a multiple of 8 rows the 128B-swizzle phase of every group is the same
+// (descriptor base_offset = (start >> 7) & 7).  Only the weight tiles stream through the ring.
+// Used for encoder.py:35-36, decoder.py:28-29 (ConvTranspose k3s1 = same neighbourhood, tap
+// offsets pad - r) and the 3x3 of residual.py:20.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_MAX_STAGES = 8;
+constexpr int CH_MAX_CHUNKS = 8;       // Cin <= 256
+constexpr int WP = 16;                 // padded tile width: 8 pixels + halo, multiple of 8
+
+struct ConvHaloParams {
+    const float *bias, *skip;
+    float *out;
+    int B, H, W, Cin, Cout;
+    int BH, BN, tiles_x, tiles_y;
+    int stages, relu, bo_mode;
+    int tap_w[9], tap_dy[9], tap_dx[9];
+};
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int bo_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((WP * 128u) >> 4) << 32;          // SBO: 8-pixel groups are one padded row apart
+    d |= (uint64_t)1 << 46;
+    if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // swizzle phase of the (unaligned) start row
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(CH_THREADS)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
+                 const ConvHaloParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+
+    const int chunks = p.Cin / 32;
+    const int halo_bytes = (p.BH + 2) * p.BN * WP * 128;        // per 32-channel chunk
+    const int b_bytes = p.Cout * 128;
+    const int S = p.stages;
+    const uint32_t ring_off = (uint32_t)(chunks * halo_bytes);
+    const uint32_t bar_off = ring_off + (uint32_t)(S * b_bytes);
+    const uint32_t bars = sbase + bar_off;
+    auto bfull = [&](int s) { return bars + 8u * s; };
+    auto bempty = [&](int s) { return bars + 8u * (CH_MAX_STAGES + s); };
+    auto hfull = [&](int c) { return bars + 8u * (2 * CH_MAX_STAGES + c); };
+    const uint32_t tfull = bars + 8u * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS);
+    const int misc = 8 * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS + 1);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + misc);
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + misc + 24);   // 16-byte aligned (misc = 200)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int tcols = 32;
+    while (tcols < p.Cout) tcols <<= 1;
+
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = tile * p.BN;
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tma_in);
+        ptx::prefetch_tmap(&tma_w);
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(bfull(s), 1); ptx::mbar_init(bempty(s), 1); }
+        for (int c = 0; c < chunks; ++c) ptx::mbar_init(hfull(c), 1);
+        ptx::mbar_init(tfull, 1);
+        ptx::fence_mbar_init();
+    }
+    for (int c = tid; c < p.Cout; c += CH_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + misc, (uint32_t)tcols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int ksteps = 9 * chunks;             // k-step i: chunk-major so the first MMAs need only chunk 0
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int c = 0; c < chunks; ++c) {
+                ptx::mbar_expect_tx(hfull(c), (uint32_t)halo_bytes);
+                ptx::tma_load_4d(sbase + c * halo_bytes, &tma_in, hfull(c), c * 32, gx0 - 1, n0, gy0 - 1);
+            }
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % S;
+                const uint32_t par = (uint32_t)((i / S) & 1);
+                const int c = i / 9, t = i - c * 9;
+                ptx::mbar_wait(bempty(s), par ^ 1);
+                ptx::mbar_expect_tx(bfull(s), (uint32_t)b_bytes);
+                ptx::tma_load_2d(sbase + ring_off + s * b_bytes, &tma_w, bfull(s), c * 32, p.tap_w[t] * p.Cout);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
+            for (int i = 0; i < ksteps; ++i) {
+                const int s = i % S;
+                const uint32_t par = (uint32_t)((i / S) & 1);
+                const int c = i / 9, t = i - c * 9;
+                if (t == 0) ptx::mbar_wait(hfull(c), 0);
+                ptx::mbar_wait(bfull(s), par);
+                ptx::tc_fence_after();
+                const uint32_t a = sbase + c * halo_bytes +
+                                   (uint32_t)(((p.tap_dy[t] + 1) * p.BN * WP + (p.tap_dx[t] + 1)) * 128);
+                const uint32_t b = sbase + ring_off + s * b_bytes;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    ptx::mma_tf32(tmem_base, halo_desc(a + kk * 32, p.bo_mode), ptx::smem_desc_sw128(b + kk * 32), idesc,
+                                  (i > 0 || kk > 0) ? 1u : 0u);
+                ptx::tc_commit(bempty(s));
+            }
+            ptx::tc_commit(tfull);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                 // = (y * BN + bn) * 8 + x
+        const int x = row & 7, g = row >> 3;
+        const int bn = g % p.BN, yy = g / p.BN;
+        const int gx = gx0 + x, gy = gy0 + yy, n = n0 + bn;
+        const bool valid = gx < p.W && gy < p.H && n < p.B;
+        const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.Cout;
+        ptx::mbar_wait(tfull, 0);
+        ptx::tc_fence_after();
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            float v[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            ptx::tmem_ld_wait32(v);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (c0 + i < p.Cout) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
+                        float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                        if (p.skip) {
+                            const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
+                            o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                        }
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+}
+
+int ch_pow2_ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+int conv_halo_mode() {          // 0 = off, 1 = on (descriptor base_offset set), 2 = on (base_offset left 0)
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("VQB_CONV_HALO");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+bool conv_halo_supported(const ConvLaunch &p) {
+    if (conv_halo_mode() == 0) return false;
+    const bool nhwc = p.in_sc == 1 && p.in_sw == p.Cin && p.out_sc == 1 && p.out_sw == p.Cout;
+    if (!nhwc || p.ntaps != 9 || p.in_step != 1 || p.out_step != 1 || p.OHg != p.H || p.OWg != p.W) return false;
+    for (int t = 0; t < 9; ++t)
+        if (p.tap_dy[t] < -1 || p.tap_dy[t] > 1 || p.tap_dx[t] < -1 || p.tap_dx[t] > 1) return false;
+    return p.Cin % 32 == 0 && p.Cin <= 32 * CH_MAX_CHUNKS && p.Cout % 16 == 0 && p.Cout >= 16 && p.Cout <= 256 &&
+           (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+           (p.skip == nullptr || (reinterpret_cast<uintptr_t>(p.skip) & 15) == 0);
+}
+
+int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) {
+    ConvHaloParams q;
+    q.bias = p.bias; q.skip = p.skip; q.out = p.out;
+    q.B = p.B; q.H = p.H; q.W = p.W; q.Cin = p.Cin; q.Cout = p.Cout; q.relu = p.relu;
+    q.BH = ch_pow2_ceil(p.H) < 16 ? ch_pow2_ceil(p.H) : 16;
+    q.BN = 16 / q.BH;
+    q.tiles_x = (p.W + 7) / 8;
+    q.tiles_y = (p.H + q.BH - 1) / q.BH;
+    const int tiles_n = (p.B + q.BN - 1) / q.BN;
+    q.bo_mode = conv_halo_mode() == 1 ? 1 : 0;
+    for (int t = 0; t < 9; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
+
+    CUtensorMap tin, tw;
+    // dims ordered (c, w, n, h): the BN images of a tile interleave row by row in shared memory
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.B, (uint64_t)p.H};
+    const uint64_t strides[3] = {(uint64_t)p.Cin * 4, (uint64_t)p.H * p.W * p.Cin * 4, (uint64_t)p.W * p.Cin * 4};
+    const uint32_t box[4] = {32u, (uint32_t)WP, (uint32_t)q.BN, (uint32_t)(q.BH + 2)};
+    const uint32_t es[4] = {1u, 1u, 1u, 1u};
+    int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.in, dims, strides, box, es,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, w_tc, (uint64_t)p.Cin, (uint64_t)9 * p.Cout,
+                            (uint64_t)p.Cin * 4, 32, (uint32_t)p.Cout, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const int chunks = p.Cin / 32;
+    const int halo_bytes = (q.BH + 2) * q.BN * WP * 128;
+    const int b_bytes = p.Cout * 128;
+    const int fixed = chunks * halo_bytes + 8 * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS + 1) + 24 + p.Cout * 4 + 1024;
+    int stages = (225 * 1024 - fixed) / b_bytes;
+    if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
+    if (stages > 9 * chunks) stages = 9 * chunks;
+    if (stages < 2) return VQB_ERR_UNSUPPORTED;
+    q.stages = stages;
+    const int smem = fixed + stages * b_bytes;
+    static int attr_max = 0;
+    if (smem > attr_max) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_max = smem;
+    }
+    const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
+    if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
+    conv_halo_kernel<<<(unsigned)grid, CH_THREADS, smem, s>>>(tin, tw, q);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}
