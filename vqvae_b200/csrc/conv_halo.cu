@@ -7,7 +7,8 @@
 // nine UMMA shared-memory descriptors into that one tile: tap (dy,dx) starts (dy+1)*BN*16+(dx+1)
 // 128-byte rows further in, 8-pixel row groups stay 16 rows (2048 B) apart, and because the
 // padded row length is a multiple of 8 rows the 128B-swizzle phase of every group is the same
-// (descriptor base_offset = (start >> 7) & 7).  Only the weight tiles stream through the ring.
+// (the descriptor's base_offset stays 0: the hardware uses absolute address bits).  Only the
+// weight tiles stream through the ring.
 // Used for encoder.py:35-36, decoder.py:28-29 (ConvTranspose k3s1 = same neighbourhood, tap
 // offsets pad - r) and the 3x3 of residual.py:20.
 #include <cstdlib>
@@ -36,7 +37,9 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int bo_mode) {
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((WP * 128u) >> 4) << 32;          // SBO: 8-pixel groups are one padded row apart
     d |= (uint64_t)1 << 46;
-    if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // swizzle phase of the (unaligned) start row
+    // base_offset (bits 49-51) stays 0: measured on B200, the tensor core derives the swizzle
+    // phase from the absolute shared-memory address; setting (saddr >> 7) & 7 breaks the result.
+    (void)bo_mode;
     d |= (uint64_t)2 << 61;
     return d;
 }
@@ -171,11 +174,11 @@ int ch_pow2_ceil(int x) {
 
 }  // namespace
 
-int conv_halo_mode() {          // 0 = off, 1 = on (descriptor base_offset set), 2 = on (base_offset left 0)
+int conv_halo_mode() {          // on by default; VQB_CONV_HALO=0 falls back to the per-tap TMA kernel (conv_tc.cu)
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("VQB_CONV_HALO");
-        mode = e ? atoi(e) : 0;
+        mode = e ? atoi(e) : 1;
     }
     return mode;
 }
@@ -200,7 +203,7 @@ int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) {
     q.tiles_x = (p.W + 7) / 8;
     q.tiles_y = (p.H + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
-    q.bo_mode = conv_halo_mode() == 1 ? 1 : 0;
+    q.bo_mode = 0;
     for (int t = 0; t < 9; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
 
     CUtensorMap tin, tw;

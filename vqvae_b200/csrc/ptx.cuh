@@ -90,6 +90,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same layout with an explicit stride between 8-row groups (operand windows inside a larger
+// shared-memory tile, e.g. a conv halo tile).  base_offset stays 0 even when saddr is not
+// 1024-byte aligned: the tensor core takes the swizzle phase from the absolute address
+// (measured: setting base_offset = (saddr >> 7) & 7 gives wrong results, see conv_halo.cu).
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor: c_format F32 (1) at [4,6); a/b format at [7,10)/[10,13)
 // (0 F16, 1 BF16, 2 TF32); a/b K-major (0) at [15]/[16]; N>>3 at [17,23); M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t ab_format, uint32_t M, uint32_t N) {

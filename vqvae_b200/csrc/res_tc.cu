@@ -6,7 +6,8 @@
 // with act = ReLU when the next consumer applies one first (always inside a ResidualStack).
 // Five PyTorch launches (relu, conv, relu, conv, add) and the (B,Cmid,H,W) intermediate's HBM
 // round trip become two chained GEMMs inside one CTA per 128-pixel tile:
-//   GEMM1  D1[128][Cmid] = sum_{9 taps, C/32 chunks} A[128][32] * W1[Cmid][32]^T   (TMA ring, as conv_tc.cu)
+//   GEMM1  D1[128][Cmid] = sum_{9 taps, C/32 chunks} A[128][32] * W1[Cmid][32]^T   (A = one halo tile per
+//          chunk, the nine taps are shifted UMMA descriptors into it, as conv_halo.cu; W1 streams)
 //   epi1   tcgen05.ld D1 -> ReLU -> written back to shared memory as the K-major, 128B-swizzled
 //          A operand of GEMM2 (one 128-byte row per pixel per 32 channels)
 //   GEMM2  D2[128][C] = A2[128][Cmid] * W2[C][Cmid]^T
@@ -19,12 +20,14 @@ namespace {
 constexpr int RT_THREADS = 256;
 constexpr int RT_MAX_STAGES = 8;
 constexpr int RT_A_BYTES = 128 * 128;
+constexpr int RT_MAX_CHUNKS = 8;
+constexpr int RT_WP = 16;              // padded tile width (8 pixels + halo), multiple of 8
 
 struct ResTcParams {
     const float *skip;      // r, NHWC (B,H,W,C)
     float *out;             // NHWC (B,H,W,C)
     int B, H, W, C, Cmid;
-    int BW, BH, BN, tiles_x, tiles_y;
+    int BH, BN, tiles_x, tiles_y;          // tile = 8 px wide x (BH rows x BN images = 16)
     int stages;
     int relu_out;
 };
@@ -38,10 +41,12 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     unsigned char *sm = smem_raw + (sbase - raw);
 
     const int S = p.stages;
-    const int b1_bytes = p.Cmid * 128;
-    const int stage_bytes = RT_A_BYTES + b1_bytes;
+    const int chunks = p.C / 32;
+    const int halo_bytes = (p.BH + 2) * p.BN * RT_WP * 128; // per 32-channel chunk
+    const int stage_bytes = p.Cmid * 128;                   // W1 tile of one (tap, chunk)
     const int matoms = p.Cmid / 32;                         // 128-byte atoms of the GEMM2 K dimension
-    const uint32_t a2_off = (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
+    const uint32_t ring_off = (uint32_t)(chunks * halo_bytes);
+    const uint32_t a2_off = ring_off + (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
     const uint32_t w2_off = a2_off + (uint32_t)(matoms * RT_A_BYTES);   // W2: matoms x [C rows][128 B]
     const uint32_t bar_off = w2_off + (uint32_t)(matoms * p.C * 128);
     const uint32_t bars = sbase + bar_off;
@@ -51,7 +56,9 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const uint32_t d1full = bars + 8u * (2 * RT_MAX_STAGES + 1);
     const uint32_t a2ready = bars + 8u * (2 * RT_MAX_STAGES + 2);
     const uint32_t d2full = bars + 8u * (2 * RT_MAX_STAGES + 3);
-    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * RT_MAX_STAGES + 4));
+    auto hfull = [&](int c) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + c); };
+    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + RT_MISC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tcols = 32;
@@ -61,7 +68,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     int tile = blockIdx.x;
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
     const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-    const int gx0 = tx * p.BW, gy0 = ty * p.BH, n0 = tile * p.BN;
+    const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = tile * p.BN;
 
     if (tid == 0) {
         ptx::prefetch_tmap(&tma_in);
@@ -72,33 +79,33 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_init(d1full, 1);
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
+        for (int c = 0; c < chunks; ++c) ptx::mbar_init(hfull(c), 1);
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * RT_MAX_STAGES + 4), (uint32_t)tcols);
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    const int kchunks = p.C / 32;
-    const int ksteps = 9 * kchunks;
+    const int ksteps = 9 * chunks;             // chunk-major: the first MMAs need only halo chunk 0
 
     if (warp == 0) {
         if (lane == 0) {
-            // W2 (all of it) once
-            ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));
+            for (int c = 0; c < chunks; ++c) {          // input tile + halo, once per 32-channel chunk
+                ptx::mbar_expect_tx(hfull(c), (uint32_t)halo_bytes);
+                ptx::tma_load_4d(sbase + c * halo_bytes, &tma_in, hfull(c), c * 32, gx0 - 1, n0, gy0 - 1);
+            }
+            ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
             for (int a = 0; a < matoms; ++a)
                 ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
-            for (int i = 0; i < ksteps; ++i) {
+            for (int i = 0; i < ksteps; ++i) {          // W1 tiles stream through the ring
                 const int s = i % S;
                 const uint32_t par = (uint32_t)((i / S) & 1);
-                const int t = i / kchunks, cc = i - t * kchunks;
-                const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
+                const int c = i / 9, t = i - c * 9;
                 ptx::mbar_wait(empty(s), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
-                const uint32_t dst = sbase + s * stage_bytes;
-                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 + dx, gy0 + dy, n0);
-                ptx::tma_load_2d(dst + RT_A_BYTES, &tma_w1, full(s), cc * 32, t * p.Cmid);
+                ptx::tma_load_2d(sbase + ring_off + s * stage_bytes, &tma_w1, full(s), c * 32, t * p.Cmid);
             }
         }
     } else if (warp == 1) {
@@ -108,13 +115,20 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             for (int i = 0; i < ksteps; ++i) {
                 const int s = i % S;
                 const uint32_t par = (uint32_t)((i / S) & 1);
+                const int c = i / 9, t = i - c * 9;
+                const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
+                if (t == 0) ptx::mbar_wait(hfull(c), 0);
                 ptx::mbar_wait(full(s), par);
                 ptx::tc_fence_after();
-                const uint32_t a = sbase + s * stage_bytes, b = a + RT_A_BYTES;
+                // tap (dy,dx) = the halo tile read (dy+1) padded rows and (dx+1) pixels further in;
+                // 8-pixel groups stay one padded row (RT_WP*128 B) apart.  base_offset stays 0: the
+                // tensor core derives the swizzle phase from the absolute shared-memory address.
+                const uint32_t a = sbase + c * halo_bytes + (uint32_t)(((dy + 1) * p.BN * RT_WP + (dx + 1)) * 128);
+                const uint32_t b = sbase + ring_off + s * stage_bytes;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128(a + kk * 32), ptx::smem_desc_sw128(b + kk * 32),
-                                  idesc1, (i > 0 || kk > 0) ? 1u : 0u);
+                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128_sbo(a + kk * 32, RT_WP * 128),
+                                  ptx::smem_desc_sw128(b + kk * 32), idesc1, (i > 0 || kk > 0) ? 1u : 0u);
                 ptx::tc_commit(empty(s));
             }
             ptx::tc_commit(d1full);
@@ -155,7 +169,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(a2ready);
 
         // ---- epilogue 2: D2 + skip -> ReLU -> NHWC store ----
-        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+        const int bw = row & 7, grp = row >> 3;             // row = (y * BN + bn) * 8 + x
+        const int bn = grp % p.BN, bh = grp / p.BN;
         const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
         const bool valid = gx < p.W && gy < p.H && n < p.B;
         const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.C;
@@ -202,17 +217,17 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     if (!res_tc_supported(C, Cmid, r, out)) return VQB_ERR_UNSUPPORTED;
     ResTcParams q;
     q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
-    q.BW = rt_pow2_ceil(W) < 16 ? rt_pow2_ceil(W) : 16;
-    q.BH = rt_pow2_ceil(H) < 128 / q.BW ? rt_pow2_ceil(H) : 128 / q.BW;
-    q.BN = 128 / (q.BW * q.BH);
-    q.tiles_x = (W + q.BW - 1) / q.BW;
+    q.BH = rt_pow2_ceil(H) < 16 ? rt_pow2_ceil(H) : 16;
+    q.BN = 16 / q.BH;
+    q.tiles_x = (W + 7) / 8;
     q.tiles_y = (H + q.BH - 1) / q.BH;
     const int tiles_n = (B + q.BN - 1) / q.BN;
 
     CUtensorMap tin, tw1, tw2;
-    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
-    const uint32_t box[4] = {32u, (uint32_t)q.BW, (uint32_t)q.BH, (uint32_t)q.BN};
+    // dims ordered (c, w, n, h): the BN images of a tile interleave row by row in shared memory
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)B, (uint64_t)H};
+    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)H * W * C * 4, (uint64_t)W * C * 4};
+    const uint32_t box[4] = {32u, (uint32_t)RT_WP, (uint32_t)q.BN, (uint32_t)(q.BH + 2)};
     const uint32_t es[4] = {1u, 1u, 1u, 1u};
     int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, r, dims, strides, box, es,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
@@ -224,11 +239,13 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
                             (uint64_t)Cmid * 4, 32, (uint32_t)C, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
-    const int stage_bytes = RT_A_BYTES + Cmid * 128;
-    const int fixed = (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 + 8 * (2 * RT_MAX_STAGES + 4) + 16 + 1024;
-    int stages = (220 * 1024 - fixed) / stage_bytes;
+    const int stage_bytes = Cmid * 128;
+    const int chunks = C / 32;
+    const int fixed = chunks * (q.BH + 2) * q.BN * RT_WP * 128 + (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 +
+                      8 * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS) + 16 + 1024;
+    int stages = (226 * 1024 - fixed) / stage_bytes;
     if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
-    if (stages > 9 * (C / 32)) stages = 9 * (C / 32);
+    if (stages > 9 * chunks) stages = 9 * chunks;
     if (stages < 2) return VQB_ERR_UNSUPPORTED;
     q.stages = stages;
     const int smem = stages * stage_bytes + fixed;
