@@ -63,9 +63,11 @@ unsigned long long vqb_launch_count(void);
  * nn.Conv2d weight (Cout,Cin,kh,kw)          encoder.py:29-36, residual.py:20-24,
  *                                            vqvae.py:16-17
  * nn.ConvTranspose2d weight (Cin,Cout,kh,kw) decoder.py:28-35   (transposed = 1)
- * -> `packed` holds 2*Cout*Cin*kh*kw floats: the tap-major GEMM operand in both
+ * -> `packed` holds 2*Cout*Cin*kh*kw + 144*Cin floats: the tap-major GEMM operand in both
  *    layouts the kernels read, [(r*kw+s)*Cin + ci][co] (FFMA path) followed by
- *    [(r*kw+s)][co][ci] (K-major rows for the tcgen05 path).                      */
+ *    [(r*kw+s)][co][ci] (K-major rows for the tcgen05 path); for a k4 s2 transposed
+ *    conv with Cout <= 4 a third region [9][16][Cin] (3x3-neighbourhood + pixel-shuffle
+ *    form of decoder.py:34-35) follows.                                           */
 int vqb_pack_conv_weight_f32(const float *w, float *packed, int Cout, int Cin, int kh,
                              int kw, int transposed, void *stream);
 

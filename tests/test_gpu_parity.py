@@ -154,6 +154,10 @@ TC_CONV_CASES = [
     (1, 32, 20, 36, 16, 3, 1, 1, False, 1, 1, False, False),   # multi-tile in x and y, Cout=16
     (5, 96, 4, 4, 64, 4, 2, 1, True, 1, 1, False, False),      # small image, 3 k-chunks, BN=8 tile
     (1, 32, 33, 17, 32, 4, 2, 1, False, 1, 1, False, False),   # odd sizes, stride 2
+    (2, 64, 16, 16, 3, 4, 2, 1, True, 1, 0, False, False),     # decoder.py:34-35: 3x3-neighbourhood GEMM + pixel shuffle
+    (1, 32, 5, 9, 2, 4, 2, 1, True, 1, 0, True, False),        # same, ragged tile, Cout=2
+    (2, 3, 32, 32, 64, 4, 2, 1, False, 0, 1, True, False),     # encoder.py:29-31: hand-built im2col tile
+    (3, 3, 12, 20, 128, 4, 2, 1, False, 0, 1, False, False),   # same, partial last tile, Cout=128
 ]
 
 

@@ -17,6 +17,12 @@ int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, fl
 bool res_tc_supported(int C, int Cmid, const void *r, const void *out);
 int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
                   int Cmid, int relu_out, cudaStream_t s);
+bool conv_in_tc_supported(int Cin, int Cout, int H, int W, const void *y);
+int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float *y, int B, int H, int W, int Cout,
+                      int relu, cudaStream_t s);
+bool convt_shuffle_supported(int Cin, int Cout, const void *in, const void *out);
+int launch_convt_shuffle(const float *in, const float *w_shuffle, const float *bias, float *out, int B, int Cin, int H,
+                         int W, int Cout, int relu, cudaStream_t s);
 bool conv_halo_supported(const ConvLaunch &p);
 int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
@@ -87,9 +93,15 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
 
     // the two HBM-bound end layers have dedicated kernels (conv_edge.cu)
     if (kh == 4 && kw == 4 && stride == 2 && pad == 1 && !skip) {
+        if (!transposed && precision != VQB_FP32 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
+            conv_in_tc_supported(Cin, Cout, H, W, out))       // tcgen05 with a hand-built im2col tile
+            return launch_conv_in_tc(in, w_packed, bias, out, B, H, W, Cout, relu, s);
         if (!transposed && Cin == 3 && Cout % 32 == 0 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
             H % 2 == 0 && W % 2 == 0 && (size_t)16 * Cin * Cout * 4 <= 48 * 1024)
             return launch_conv_in_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
+        if (transposed && precision != VQB_FP32 && in_layout == VQB_NHWC && out_layout == VQB_NCHW &&
+            convt_shuffle_supported(Cin, Cout, in, out))      // tcgen05: one 3x3-neighbourhood GEMM + pixel shuffle
+            return launch_convt_shuffle(in, w_packed + (size_t)2 * 16 * Cin * Cout, bias, out, B, Cin, H, W, Cout, relu, s);
         if (transposed && Cout == 3 && Cin % 4 == 0 && Cin <= 128 && ((Cin / 4) & (Cin / 4 - 1)) == 0 &&
             in_layout == VQB_NHWC && out_layout == VQB_NCHW)
             return launch_convt_out_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);

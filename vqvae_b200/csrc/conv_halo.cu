@@ -29,6 +29,8 @@ struct ConvHaloParams {
     int B, H, W, Cin, Cout;
     int BH, BN, tiles_x, tiles_y;
     int stages, relu, bo_mode;
+    int shuffle_cout;       // > 0: the GEMM's 16 columns are (py, px, co) of a k4s2p1 transposed conv with this
+                            // many real output channels; the epilogue pixel-shuffles them into the NCHW output
     int tap_w[9], tap_dy[9], tap_dx[9];
 };
 
@@ -84,7 +86,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
         ptx::mbar_init(tfull, 1);
         ptx::fence_mbar_init();
     }
-    for (int c = tid; c < p.Cout; c += CH_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    for (int c = tid; c < p.Cout; c += CH_THREADS) {
+        if (p.shuffle_cout > 0) bias_s[c] = (p.bias && c < 4 * p.shuffle_cout) ? __ldg(p.bias + c % p.shuffle_cout) : 0.f;
+        else bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    }
     if (warp == 2) ptx::tmem_alloc(sbase + bar_off + misc, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
@@ -138,6 +143,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
         const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.Cout;
         ptx::mbar_wait(tfull, 0);
         ptx::tc_fence_after();
+        if (p.shuffle_cout > 0) {
+            // decoder.py:34-35 as a 3x3-neighbourhood GEMM: column (py*2+px)*Cout+co of input pixel (gy,gx)
+            // is output pixel (2gy+py, 2gx+px), channel co, of the NCHW module output.
+            float v[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+            ptx::tmem_ld_wait32(v);
+            if (valid) {
+                const int co_n = p.shuffle_cout, OH = 2 * p.H, OW = 2 * p.W;
+                for (int co = 0; co < co_n; ++co)
+#pragma unroll
+                    for (int py = 0; py < 2; ++py) {
+                        float2 o = make_float2(v[(py * 2 + 0) * co_n + co] + bias_s[co],
+                                               v[(py * 2 + 1) * co_n + co] + bias_s[co]);
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                        *reinterpret_cast<float2 *>(p.out + (((long long)n * co_n + co) * OH + 2 * gy + py) * OW + 2 * gx) = o;
+                    }
+            }
+        } else
         for (int c0 = 0; c0 < p.Cout; c0 += 32) {
             float v[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -194,7 +217,10 @@ bool conv_halo_supported(const ConvLaunch &p) {
            (p.skip == nullptr || (reinterpret_cast<uintptr_t>(p.skip) & 15) == 0);
 }
 
-int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) {
+int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout, cudaStream_t s);
+int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) { return launch_conv_halo_ex(p, w_tc, 0, s); }
+
+int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout, cudaStream_t s) {
     ConvHaloParams q;
     q.bias = p.bias; q.skip = p.skip; q.out = p.out;
     q.B = p.B; q.H = p.H; q.W = p.W; q.Cin = p.Cin; q.Cout = p.Cout; q.relu = p.relu;
@@ -204,6 +230,7 @@ int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) {
     q.tiles_y = (p.H + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
     q.bo_mode = 0;
+    q.shuffle_cout = shuffle_cout;
     for (int t = 0; t < 9; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
 
     CUtensorMap tin, tw;
@@ -239,4 +266,24 @@ int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s) {
     conv_halo_kernel<<<(unsigned)grid, CH_THREADS, smem, s>>>(tin, tw, q);
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
+}
+
+// ConvTranspose2d(Cin -> Cout <= 4, k4 s2 p1), NHWC in -> NCHW out, as ONE 3x3-neighbourhood GEMM with 16 columns
+// (py, px, co): w_shuffle = [9 taps][16][Cin] packed by vqb_pack_conv_weight_f32 (third region).
+bool convt_shuffle_supported(int Cin, int Cout, const void *in, const void *out) {
+    return conv_halo_mode() != 0 && Cin % 32 == 0 && Cin <= 32 * CH_MAX_CHUNKS && Cout >= 1 && Cout <= 4 &&
+           (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+}
+
+int launch_convt_shuffle(const float *in, const float *w_shuffle, const float *bias, float *out, int B, int Cin, int H,
+                         int W, int Cout, int relu, cudaStream_t s) {
+    ConvLaunch p;
+    p.in = in; p.w = nullptr; p.bias = bias; p.skip = nullptr; p.out = out;
+    p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = 16; p.relu = relu;
+    p.OHg = H; p.OWg = W; p.in_step = 1; p.out_step = 1; p.out_py = 0; p.out_px = 0;
+    p.ntaps = 9;
+    for (int t = 0; t < 9; ++t) { p.tap_w[t] = t; p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; }
+    p.in_sc = 1; p.in_sw = Cin; p.in_sh = (long long)W * Cin; p.in_sn = (long long)H * W * Cin;
+    p.out_sc = 1; p.out_sw = 16; p.out_sh = 0; p.out_sn = 0;      // unused by the shuffle epilogue
+    return launch_conv_halo_ex(p, w_shuffle, Cout, s);
 }

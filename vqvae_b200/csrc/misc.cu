@@ -24,6 +24,24 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, float *__restric
     }
 }
 
+// ConvTranspose2d k4 s2 p1 weight (Cin,Cout,4,4), Cout <= 4  ->  [9 neighbour taps (dy,dx)][16][Cin]:
+// row (py*2+px)*Cout+co of tap (dy,dx) holds W[ci][co][py-2dy+1][px-2dx+1] when that kernel index
+// exists (the neighbour contributes to that output phase), else 0.  See conv_halo.cu.
+__global__ void pack_convt_shuffle_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin) {
+    const int total = 9 * 16 * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Cin, row = (i / Cin) % 16, tap = i / (16 * Cin);
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        float v = 0.f;
+        if (row < 4 * Cout) {
+            const int co = row % Cout, ph = row / Cout, py = ph >> 1, px = ph & 1;
+            const int kh = py - 2 * dy + 1, kw = px - 2 * dx + 1;
+            if (kh >= 0 && kh < 4 && kw >= 0 && kw < 4) v = w[(((size_t)ci * Cout + co) * 4 + kh) * 4 + kw];
+        }
+        out[i] = v;
+    }
+}
+
 // tiled transpose of the innermost two logical axes: in[b][R][Ccols] -> out[b][Ccols][R]
 __global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int R, int Cc) {
     __shared__ float tile[32][33];
@@ -123,6 +141,11 @@ extern "C" int vqb_pack_conv_weight_f32(const float *w, float *packed, int Cout,
     const long long total = (long long)Cout * Cin * kh * kw;
     pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, packed, Cout, Cin, kh, kw,
                                                                               transposed);
+    if (transposed && kh == 4 && kw == 4 && Cout <= 4) {
+        pack_convt_shuffle_kernel<<<grid_for(9 * 16 * Cin, 256), 256, 0, (cudaStream_t)stream>>>(w, packed + 2 * total,
+                                                                                               Cout, Cin);
+        VQB_COUNT_LAUNCH(1);
+    }
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -103,6 +103,7 @@ __global__ void vq_tc_prep_kernel(const float *__restrict__ E, int K, int Kpad, 
     else atomicMax(&scal[0], __float_as_uint(sqrtf(s) * 1.00001f));       // positive floats order as uints
 }
 
+template <bool kDebug>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme,
              const __grid_constant__ CUtensorMap tmq, const VqTcParams p) {
@@ -287,7 +288,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         const float s2 = fmaf(v[g * 8 + 2], -2.f, b0.z), s3 = fmaf(v[g * 8 + 3], -2.f, b0.w);
                         const float s4 = fmaf(v[g * 8 + 4], -2.f, b1.x), s5 = fmaf(v[g * 8 + 5], -2.f, b1.y);
                         const float s6 = fmaf(v[g * 8 + 6], -2.f, b1.z), s7 = fmaf(v[g * 8 + 7], -2.f, b1.w);
-                        if (p.dbg) {
+                        if (kDebug && p.dbg) {
                             const long long grow = tile * TM + row;
                             if (grow < p.N) {
                                 float *dst = p.dbg + (size_t)grow * Kpad + c * CN + h * 128 + j * 32 + g * 8;
@@ -567,7 +568,9 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
 
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        e = cudaFuncSetAttribute(vq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(vq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -585,7 +588,8 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
         const char *fl = getenv("VQB_TC_FLAGS");
         p.flags = fl ? atoi(fl) : 0;
     }
-    vq_tc_kernel<<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
+    if (dbg) vq_tc_kernel<true><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
+    else vq_tc_kernel<false><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
     VQB_COUNT_LAUNCH(3);
     return vqb_cuda_status(cudaGetLastError());

@@ -63,7 +63,8 @@ def pack_conv_weight(w, transposed):
         cin, cout, kh, kw = w.shape
     else:
         cout, cin, kh, kw = w.shape
-    out = torch.empty((2, kh * kw * cin * cout), dtype=torch.float32, device=w.device)
+    # 2 GEMM layouts + (for the k4s2 output layer) the 9x16xCin pixel-shuffle packing
+    out = torch.empty((2 * kh * kw * cin * cout + 9 * 16 * cin,), dtype=torch.float32, device=w.device)
     check(lib().vqb_pack_conv_weight_f32(w.data_ptr(), out.data_ptr(), cout, cin, kh, kw,
                                          int(bool(transposed)), _stream()), "pack_conv_weight")
     return out
