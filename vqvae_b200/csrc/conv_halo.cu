@@ -19,7 +19,9 @@
 namespace {
 
 constexpr int CH_THREADS = 256;
-constexpr int CH_MAX_STAGES = 8;
+constexpr int CH_MAX_STAGES = 32;     // weight-tile ring: as deep as shared memory allows (the k-loop is
+                                      // bound by bytes in flight, not by bandwidth)
+constexpr int CH_HALO_BUFS = 2;       // halo tiles are double buffered: chunk c+2 loads while c+1 computes
 constexpr int CH_MAX_CHUNKS = 8;       // Cin <= 256
 constexpr int WP = 16;                 // padded tile width: 8 pixels + halo, multiple of 8
 
@@ -58,16 +60,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     const int halo_bytes = (p.BH + 2) * p.BN * WP * 128;        // per 32-channel chunk
     const int b_bytes = p.Cout * 128;
     const int S = p.stages;
-    const uint32_t ring_off = (uint32_t)(chunks * halo_bytes);
+    const int hbufs = chunks < CH_HALO_BUFS ? chunks : CH_HALO_BUFS;
+    const uint32_t ring_off = (uint32_t)(hbufs * halo_bytes);
     const uint32_t bar_off = ring_off + (uint32_t)(S * b_bytes);
     const uint32_t bars = sbase + bar_off;
     auto bfull = [&](int s) { return bars + 8u * s; };
     auto bempty = [&](int s) { return bars + 8u * (CH_MAX_STAGES + s); };
-    auto hfull = [&](int c) { return bars + 8u * (2 * CH_MAX_STAGES + c); };
-    const uint32_t tfull = bars + 8u * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS);
-    const int misc = 8 * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS + 1);
+    auto hfull = [&](int b) { return bars + 8u * (2 * CH_MAX_STAGES + b); };
+    auto hempty = [&](int b) { return bars + 8u * (2 * CH_MAX_STAGES + CH_HALO_BUFS + b); };
+    const uint32_t tfull = bars + 8u * (2 * CH_MAX_STAGES + 2 * CH_HALO_BUFS);
+    const int misc = 8 * (2 * CH_MAX_STAGES + 2 * CH_HALO_BUFS + 1);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + misc);
-    float *bias_s = reinterpret_cast<float *>(sm + bar_off + misc + 24);   // 16-byte aligned (misc = 200)
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + misc + 8);    // 16-byte aligned (misc % 16 == 8)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tcols = 32;
@@ -82,7 +86,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
         ptx::prefetch_tmap(&tma_in);
         ptx::prefetch_tmap(&tma_w);
         for (int s = 0; s < S; ++s) { ptx::mbar_init(bfull(s), 1); ptx::mbar_init(bempty(s), 1); }
-        for (int c = 0; c < chunks; ++c) ptx::mbar_init(hfull(c), 1);
+        for (int b = 0; b < CH_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
         ptx::mbar_init(tfull, 1);
         ptx::fence_mbar_init();
     }
@@ -99,14 +103,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     const int ksteps = 9 * chunks;             // k-step i: chunk-major so the first MMAs need only chunk 0
     if (warp == 0) {
         if (lane == 0) {
-            for (int c = 0; c < chunks; ++c) {
-                ptx::mbar_expect_tx(hfull(c), (uint32_t)halo_bytes);
-                ptx::tma_load_4d(sbase + c * halo_bytes, &tma_in, hfull(c), c * 32, gx0 - 1, n0, gy0 - 1);
-            }
+            auto load_halo = [&](int c) {
+                const int b = c % CH_HALO_BUFS;
+                if (c >= CH_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / CH_HALO_BUFS) - 1) & 1));
+                ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
+                ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+            };
+            for (int c = 0; c < hbufs; ++c) load_halo(c);
             for (int i = 0; i < ksteps; ++i) {
                 const int s = i % S;
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
+                // refill the halo buffer chunk c-1 just vacated with chunk c+1 (the ring keeps the MMAs fed)
+                if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= CH_HALO_BUFS) load_halo(c + 1);
                 ptx::mbar_wait(bempty(s), par ^ 1);
                 ptx::mbar_expect_tx(bfull(s), (uint32_t)b_bytes);
                 ptx::tma_load_2d(sbase + ring_off + s * b_bytes, &tma_w, bfull(s), c * 32, p.tap_w[t] * p.Cout);
@@ -119,10 +128,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                 const int s = i % S;
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
-                if (t == 0) ptx::mbar_wait(hfull(c), 0);
+                const int hb = c % CH_HALO_BUFS;
+                if (t == 0) ptx::mbar_wait(hfull(hb), (uint32_t)((c / CH_HALO_BUFS) & 1));
                 ptx::mbar_wait(bfull(s), par);
                 ptx::tc_fence_after();
-                const uint32_t a = sbase + c * halo_bytes +
+                const uint32_t a = sbase + hb * halo_bytes +
                                    (uint32_t)(((p.tap_dy[t] + 1) * p.BN * WP + (p.tap_dx[t] + 1)) * 128);
                 const uint32_t b = sbase + ring_off + s * b_bytes;
 #pragma unroll
@@ -130,6 +140,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                     ptx::mma_tf32(tmem_base, halo_desc(a + kk * 32, p.bo_mode), ptx::smem_desc_sw128(b + kk * 32), idesc,
                                   (i > 0 || kk > 0) ? 1u : 0u);
                 ptx::tc_commit(bempty(s));
+                if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
             }
             ptx::tc_commit(tfull);
         }
@@ -248,8 +259,9 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     const int chunks = p.Cin / 32;
     const int halo_bytes = (q.BH + 2) * q.BN * WP * 128;
     const int b_bytes = p.Cout * 128;
-    const int fixed = chunks * halo_bytes + 8 * (2 * CH_MAX_STAGES + CH_MAX_CHUNKS + 1) + 24 + p.Cout * 4 + 1024;
-    int stages = (225 * 1024 - fixed) / b_bytes;
+    const int hbufs = chunks < CH_HALO_BUFS ? chunks : CH_HALO_BUFS;
+    const int fixed = hbufs * halo_bytes + 8 * (2 * CH_MAX_STAGES + 2 * CH_HALO_BUFS + 1) + 8 + 256 * 4 + 1024;
+    int stages = (226 * 1024 - fixed) / b_bytes;
     if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
     if (stages > 9 * chunks) stages = 9 * chunks;
     if (stages < 2) return VQB_ERR_UNSUPPORTED;

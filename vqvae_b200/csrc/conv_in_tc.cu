@@ -61,7 +61,8 @@ conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, con
         const int oy = (int)(t % OH);
         const int n = (int)(t / OH);
         unsigned char *arow = sm + atom * 16384 + row * 128;
-#pragma unroll 4
+        float vals[32];                      // all 32 gathers in flight before the first store
+#pragma unroll
         for (int kk = 0; kk < 32; ++kk) {
             const int k = atom * 32 + kk;
             float v = 0.f;
@@ -70,8 +71,12 @@ conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, con
                 const int iy = 2 * oy - 1 + (tap >> 2), ix = 2 * ox - 1 + (tap & 3);
                 if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)n * 3 + c) * H + iy) * W + ix);
             }
-            *reinterpret_cast<float *>(arow + (((kk >> 2) ^ (row & 7)) << 4) + (kk & 3) * 4) = v;
+            vals[kk] = v;
         }
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+            *reinterpret_cast<float4 *>(arow + ((c16 ^ (row & 7)) << 4)) =
+                make_float4(vals[c16 * 4], vals[c16 * 4 + 1], vals[c16 * 4 + 2], vals[c16 * 4 + 3]);
     }
     ptx::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
     ptx::tc_fence_before();

@@ -18,7 +18,8 @@
 namespace {
 
 constexpr int RT_THREADS = 256;
-constexpr int RT_MAX_STAGES = 8;
+constexpr int RT_MAX_STAGES = 32;     // W1 tile ring, as deep as shared memory allows
+constexpr int RT_HALO_BUFS = 2;       // double-buffered halo tiles
 constexpr int RT_A_BYTES = 128 * 128;
 constexpr int RT_MAX_CHUNKS = 8;
 constexpr int RT_WP = 16;              // padded tile width (8 pixels + halo), multiple of 8
@@ -45,7 +46,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const int halo_bytes = (p.BH + 2) * p.BN * RT_WP * 128; // per 32-channel chunk
     const int stage_bytes = p.Cmid * 128;                   // W1 tile of one (tap, chunk)
     const int matoms = p.Cmid / 32;                         // 128-byte atoms of the GEMM2 K dimension
-    const uint32_t ring_off = (uint32_t)(chunks * halo_bytes);
+    const int hbufs = chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS;
+    const uint32_t ring_off = (uint32_t)(hbufs * halo_bytes);
     const uint32_t a2_off = ring_off + (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
     const uint32_t w2_off = a2_off + (uint32_t)(matoms * RT_A_BYTES);   // W2: matoms x [C rows][128 B]
     const uint32_t bar_off = w2_off + (uint32_t)(matoms * p.C * 128);
@@ -56,8 +58,9 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const uint32_t d1full = bars + 8u * (2 * RT_MAX_STAGES + 1);
     const uint32_t a2ready = bars + 8u * (2 * RT_MAX_STAGES + 2);
     const uint32_t d2full = bars + 8u * (2 * RT_MAX_STAGES + 3);
-    auto hfull = [&](int c) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + c); };
-    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS);
+    auto hfull = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + b); };
+    auto hempty = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + RT_HALO_BUFS + b); };
+    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_HALO_BUFS);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + RT_MISC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -79,7 +82,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_init(d1full, 1);
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
-        for (int c = 0; c < chunks; ++c) ptx::mbar_init(hfull(c), 1);
+        for (int b = 0; b < RT_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
@@ -92,10 +95,13 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int c = 0; c < chunks; ++c) {          // input tile + halo, once per 32-channel chunk
-                ptx::mbar_expect_tx(hfull(c), (uint32_t)halo_bytes);
-                ptx::tma_load_4d(sbase + c * halo_bytes, &tma_in, hfull(c), c * 32, gx0 - 1, n0, gy0 - 1);
-            }
+            auto load_halo = [&](int c) {               // input tile + halo of one 32-channel chunk
+                const int b = c % RT_HALO_BUFS;
+                if (c >= RT_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / RT_HALO_BUFS) - 1) & 1));
+                ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
+                ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+            };
+            for (int c = 0; c < hbufs; ++c) load_halo(c);
             ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
             for (int a = 0; a < matoms; ++a)
                 ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
@@ -103,6 +109,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const int s = i % S;
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
+                if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= RT_HALO_BUFS) load_halo(c + 1);
                 ptx::mbar_wait(empty(s), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
                 ptx::tma_load_2d(sbase + ring_off + s * stage_bytes, &tma_w1, full(s), c * 32, t * p.Cmid);
@@ -117,19 +124,21 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
                 const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
-                if (t == 0) ptx::mbar_wait(hfull(c), 0);
+                const int hb = c % RT_HALO_BUFS;
+                if (t == 0) ptx::mbar_wait(hfull(hb), (uint32_t)((c / RT_HALO_BUFS) & 1));
                 ptx::mbar_wait(full(s), par);
                 ptx::tc_fence_after();
                 // tap (dy,dx) = the halo tile read (dy+1) padded rows and (dx+1) pixels further in;
                 // 8-pixel groups stay one padded row (RT_WP*128 B) apart.  base_offset stays 0: the
                 // tensor core derives the swizzle phase from the absolute shared-memory address.
-                const uint32_t a = sbase + c * halo_bytes + (uint32_t)(((dy + 1) * p.BN * RT_WP + (dx + 1)) * 128);
+                const uint32_t a = sbase + hb * halo_bytes + (uint32_t)(((dy + 1) * p.BN * RT_WP + (dx + 1)) * 128);
                 const uint32_t b = sbase + ring_off + s * stage_bytes;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128_sbo(a + kk * 32, RT_WP * 128),
                                   ptx::smem_desc_sw128(b + kk * 32), idesc1, (i > 0 || kk > 0) ? 1u : 0u);
                 ptx::tc_commit(empty(s));
+                if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
             }
             ptx::tc_commit(d1full);
             // GEMM2 once the epilogue has written relu(D1) as the A2 operand
@@ -241,8 +250,9 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
 
     const int stage_bytes = Cmid * 128;
     const int chunks = C / 32;
-    const int fixed = chunks * (q.BH + 2) * q.BN * RT_WP * 128 + (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 +
-                      8 * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS) + 16 + 1024;
+    const int hbufs = chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS;
+    const int fixed = hbufs * (q.BH + 2) * q.BN * RT_WP * 128 + (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 +
+                      8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_HALO_BUFS) + 16 + 1024;
     int stages = (226 * 1024 - fixed) / stage_bytes;
     if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
     if (stages > 9 * chunks) stages = 9 * chunks;
