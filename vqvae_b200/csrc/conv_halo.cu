@@ -21,6 +21,7 @@ namespace {
 constexpr int CH_THREADS = 256;
 constexpr int CH_MAX_STAGES = 32;     // weight-tile ring: as deep as shared memory allows (the k-loop is
                                       // bound by bytes in flight, not by bandwidth)
+constexpr int CH_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int CH_HALO_BUFS = 2;       // halo tiles are double buffered: chunk c+2 loads while c+1 computes
 constexpr int CH_MAX_CHUNKS = 8;       // Cin <= 256
 constexpr int WP = 16;                 // padded tile width: 8 pixels + halo, multiple of 8
@@ -116,7 +117,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                 const int c = i / 9, t = i - c * 9;
                 // refill the halo buffer chunk c-1 just vacated with chunk c+1 (the ring keeps the MMAs fed)
                 if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= CH_HALO_BUFS) load_halo(c + 1);
-                ptx::mbar_wait(bempty(s), par ^ 1);
+                if (s % CH_GROUP == 0) ptx::mbar_wait(bempty(s / CH_GROUP), par ^ 1);
                 ptx::mbar_expect_tx(bfull(s), (uint32_t)b_bytes);
                 ptx::tma_load_2d(sbase + ring_off + s * b_bytes, &tma_w, bfull(s), c * 32, p.tap_w[t] * p.Cout);
             }
@@ -139,7 +140,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                 for (int kk = 0; kk < 4; ++kk)
                     ptx::mma_tf32(tmem_base, halo_desc(a + kk * 32, p.bo_mode), ptx::smem_desc_sw128(b + kk * 32), idesc,
                                   (i > 0 || kk > 0) ? 1u : 0u);
-                ptx::tc_commit(bempty(s));
+                if (s % CH_GROUP == CH_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(bempty(s / CH_GROUP));
                 if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
             }
             ptx::tc_commit(tfull);
@@ -263,8 +264,9 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     const int fixed = hbufs * halo_bytes + 8 * (2 * CH_MAX_STAGES + 2 * CH_HALO_BUFS + 1) + 8 + 256 * 4 + 1024;
     int stages = (226 * 1024 - fixed) / b_bytes;
     if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
-    if (stages > 9 * chunks) stages = 9 * chunks;
-    if (stages < 2) return VQB_ERR_UNSUPPORTED;
+    if (stages >= 9 * chunks) stages = 9 * chunks;
+    else stages -= stages % CH_GROUP;             // a reused ring must hold whole commit groups
+    if (stages < CH_GROUP) return VQB_ERR_UNSUPPORTED;
     q.stages = stages;
     const int smem = fixed + stages * b_bytes;
     static int attr_max = 0;

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int CT_THREADS = 256;
 constexpr int CT_MAX_STAGES = 8;
+constexpr int CT_GROUP = 2;            // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int A_BYTES = 128 * 128;                 // 128 pixels x 32 fp32
 
 struct ConvTcParams {
@@ -93,7 +94,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
                 const int s = i % CT_STAGES;
                 const uint32_t par = (uint32_t)((i / CT_STAGES) & 1);
                 const int t = i / kchunks, cc = i - t * kchunks;
-                ptx::mbar_wait(empty(s), par ^ 1);
+                if (s % CT_GROUP == 0) ptx::mbar_wait(empty(s / CT_GROUP), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
                 const uint32_t dst = sbase + s * stage_bytes;
                 ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 * p.in_step + p.tap_dx[ph][t],
@@ -114,7 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
                 for (int kk = 0; kk < 4; ++kk)
                     ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128(a + kk * 32), ptx::smem_desc_sw128(b + kk * 32),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                ptx::tc_commit(empty(s));
+                if (s % CT_GROUP == CT_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(empty(s / CT_GROUP));
             }
             ptx::tc_commit(tfull);
         }
@@ -231,6 +232,7 @@ int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_t
     int stages = (200 * 1024) / stage_bytes;      // deep ring: the k-loop is TMA-latency bound
     if (stages > CT_MAX_STAGES) stages = CT_MAX_STAGES;
     if (stages > maxk) stages = maxk;
+    else stages -= stages % CT_GROUP;             // a reused ring must hold whole commit groups
     if (stages < 1) stages = 1;
     q.stages = stages;
     const int smem = stages * stage_bytes + 192 + p.Cout * 4 + 1024;

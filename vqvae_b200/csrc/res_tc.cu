@@ -19,6 +19,7 @@ namespace {
 
 constexpr int RT_THREADS = 256;
 constexpr int RT_MAX_STAGES = 32;     // W1 tile ring, as deep as shared memory allows
+constexpr int RT_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int RT_HALO_BUFS = 2;       // double-buffered halo tiles
 constexpr int RT_A_BYTES = 128 * 128;
 constexpr int RT_MAX_CHUNKS = 8;
@@ -110,7 +111,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
                 if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= RT_HALO_BUFS) load_halo(c + 1);
-                ptx::mbar_wait(empty(s), par ^ 1);
+                if (s % RT_GROUP == 0) ptx::mbar_wait(empty(s / RT_GROUP), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
                 ptx::tma_load_2d(sbase + ring_off + s * stage_bytes, &tma_w1, full(s), c * 32, t * p.Cmid);
             }
@@ -137,7 +138,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 for (int kk = 0; kk < 4; ++kk)
                     ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128_sbo(a + kk * 32, RT_WP * 128),
                                   ptx::smem_desc_sw128(b + kk * 32), idesc1, (i > 0 || kk > 0) ? 1u : 0u);
-                ptx::tc_commit(empty(s));
+                if (s % RT_GROUP == RT_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(empty(s / RT_GROUP));
                 if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
             }
             ptx::tc_commit(d1full);
@@ -255,8 +256,9 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
                       8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_HALO_BUFS) + 16 + 1024;
     int stages = (226 * 1024 - fixed) / stage_bytes;
     if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
-    if (stages > 9 * chunks) stages = 9 * chunks;
-    if (stages < 2) return VQB_ERR_UNSUPPORTED;
+    if (stages >= 9 * chunks) stages = 9 * chunks;
+    else stages -= stages % RT_GROUP;             // a reused ring must hold whole commit groups
+    if (stages < RT_GROUP) return VQB_ERR_UNSUPPORTED;
     q.stages = stages;
     const int smem = stages * stage_bytes + fixed;
     static int attr_max = 0;

@@ -175,11 +175,12 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     const int es = resident ? c : (int)(gc & 1);
                     const uint32_t par = resident ? 0u : (uint32_t)((gc >> 1) & 1);
                     ptx::mbar_wait(bar(E_EMPTY + es), par ^ 1);
-                    ptx::mbar_expect_tx(bar(E_FULL + es), ESTAGE + CN * 4);
+                    ptx::mbar_expect_tx(bar(E_FULL + es), resident ? ESTAGE : ESTAGE + CN * 4);
                     const uint32_t edst = sbase + OFF_E + es * ESTAGE;
                     ptx::tma_load_2d(edst, &tme, bar(E_FULL + es), 0, c * CN);
                     ptx::tma_load_2d(edst + EATOM, &tme, bar(E_FULL + es), 32, c * CN);
-                    ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
+                    if (!resident)      // resident codebooks get their norms computed in-kernel (below)
+                        ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
                 }
             }
             // `it` tiles were issued; the last (up to) two are still to be stored
@@ -228,8 +229,50 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
         const int row = q * 32 + lane;          // accumulator row = TMEM lane
         const int rsw = row & 7;
         const float INF = __int_as_float(0x7f800000);
-        const float Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
-        const bool bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
+        float Emax;
+        bool bad_codebook;
+        if (resident) {
+            // The <= 512 resident codes: canonical ||e_k||^2 (quantizer.py:50), their maximum and a
+            // non-finite flag, computed once per CTA from the shared-memory copy (no prep launch).
+            float *xred = reinterpret_cast<float *>(sm + OFF_XBD);      // scratch before the first tile
+            float mymax = 0.f;
+            unsigned mybad = 0u;
+            for (int c = 0; c < nchunks; ++c) ptx::mbar_wait(bar(E_FULL + c), 0);
+            for (int k = et; k < nchunks * CN; k += 256) {
+                float sn = INF;
+                if (k < p.K) {
+                    const unsigned char *er = sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128;
+                    sn = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 v = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ (k & 7)) << 4));
+                            sn = __fadd_rn(sn, __fmul_rn(v.x, v.x)); sn = __fadd_rn(sn, __fmul_rn(v.y, v.y));
+                            sn = __fadd_rn(sn, __fmul_rn(v.z, v.z)); sn = __fadd_rn(sn, __fmul_rn(v.w, v.w));
+                        }
+                    if (!(sn < INF)) mybad = 1u;
+                    else mymax = fmaxf(mymax, sqrtf(sn) * 1.00001f);
+                }
+                bsm[k] = sn;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, off));
+                mybad |= __shfl_xor_sync(0xffffffffu, mybad, off);
+            }
+            if (lane == 0) { xred[warp - 4] = mymax; xred[8 + warp - 4] = __uint_as_float(mybad); }
+            ptx::named_bar_sync(5, 256);
+            float mx = 0.f;
+            unsigned bad = 0u;
+            for (int w = 0; w < 8; ++w) { mx = fmaxf(mx, xred[w]); bad |= __float_as_uint(xred[8 + w]); }
+            ptx::named_bar_sync(5, 256);            // xred (= xbd) is reused by the tile loop
+            Emax = mx;
+            bad_codebook = bad != 0u;
+        } else {
+            Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
+            bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
+        }
         float2 *lists = reinterpret_cast<float2 *>(sm + OFF_LIST);
         float *xmin = reinterpret_cast<float *>(sm + OFF_XMIN);
         int *xnc = reinterpret_cast<int *>(sm + OFF_XMIN);
@@ -562,9 +605,13 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
 
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)K, s);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(scal, 0, 256, s);
-    if (e != cudaSuccess) return (int)e;
-    vq_tc_prep_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(E, K, Kpad, bn, scal);
+    int nlaunch = 2;
+    if (nchunks > 2) {          // streamed codebook: norms / max / flag from a prep launch
+        e = cudaMemsetAsync(scal, 0, 256, s);
+        if (e != cudaSuccess) return (int)e;
+        vq_tc_prep_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(E, K, Kpad, bn, scal);
+        nlaunch = 3;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -591,6 +638,6 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     if (dbg) vq_tc_kernel<true><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     else vq_tc_kernel<false><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
-    VQB_COUNT_LAUNCH(3);
+    VQB_COUNT_LAUNCH(nlaunch);
     return vqb_cuda_status(cudaGetLastError());
 }
