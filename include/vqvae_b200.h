@@ -148,6 +148,10 @@ int vqb_gather_rows_f32(const int64_t *idx, const float *codebook, int64_t N, in
  * the caller's tensor when a ResidualLayer is called directly.         */
 int vqb_relu_f32(float *x, int64_t n, void *stream);
 
+/* Diagnostic: copy the first n (<= 32) entries of the in-kernel timeline (globaltimer ns of CTA 0
+ * of the last fused residual kernel) to host memory.  Synchronises the device.          */
+int vqb_debug_read_trace(unsigned long long *dst, int n);
+
 /* ---- layout changes at the module boundary (quantizer.py:45, :74) ---------------- */
 int vqb_nchw_to_nhwc_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);
 int vqb_nhwc_to_nchw_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);

@@ -41,6 +41,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Waiting variant for warps that wait LONG (an epilogue waiting for a whole GEMM): back off with
+// nanosleep between polls.  On sm_100 the warp scheduler favours higher warp ids, so a tight poll
+// loop in an epilogue warp starves the single-thread TMA / MMA issuers sharing its SM sub-partition
+// (measured: profiles/r01_res_tc_timeline.txt -- an empty 36-iteration issue loop took 10 us).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns = 256) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

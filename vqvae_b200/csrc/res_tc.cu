@@ -12,8 +12,24 @@
 //          A operand of GEMM2 (one 128-byte row per pixel per 32 channels)
 //   GEMM2  D2[128][C] = A2[128][Cmid] * W2[C][Cmid]^T
 //   epi2   tcgen05.ld D2 -> + r (skip, from global/L2) -> ReLU -> NHWC store
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
+
+// in-kernel timeline of CTA 0 (globaltimer ns), read back with vqb_debug_read_trace (diagnostic only)
+__device__ unsigned long long g_vqb_trace[32];
+__device__ __forceinline__ void trace_mark(int i) {
+    if (blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_vqb_trace[i] = t;
+    }
+}
+extern "C" int vqb_debug_read_trace(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 32) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_vqb_trace, sizeof(unsigned long long) * n));
+}
 
 namespace {
 
@@ -32,6 +48,7 @@ struct ResTcParams {
     int BH, BN, tiles_x, tiles_y;          // tile = 8 px wide x (BH rows x BN images = 16)
     int stages;
     int relu_out;
+    int flags;              // perf experiments (env VQB_RES_FLAGS): 1 = skip GEMM1 MMAs, 2 = skip W1 loads/waits
 };
 
 __global__ void __launch_bounds__(RT_THREADS)
@@ -65,6 +82,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + RT_MISC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 128) trace_mark(0);                     // kernel entry
     int tcols = 32;
     while (tcols < p.Cmid + p.C) tcols <<= 1;
     const uint32_t d2col = (uint32_t)p.Cmid;                // D1 at column 0, D2 right after it
@@ -86,15 +104,19 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         for (int b = 0; b < RT_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
+    if (warp == 6) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
     const int ksteps = 9 * chunks;             // chunk-major: the first MMAs need only halo chunk 0
 
-    if (warp == 0) {
+    // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 MMA issuer, 6 TMEM
+    // allocator.  The single-thread issuers get the HIGHER warp ids of their sub-partitions on purpose:
+    // the scheduler favours high warp ids, and the epilogue warps poll barriers for most of the kernel.
+    if (warp == 4) {
         if (lane == 0) {
             auto load_halo = [&](int c) {               // input tile + halo of one 32-channel chunk
                 const int b = c % RT_HALO_BUFS;
@@ -111,12 +133,13 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const uint32_t par = (uint32_t)((i / S) & 1);
                 const int c = i / 9, t = i - c * 9;
                 if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= RT_HALO_BUFS) load_halo(c + 1);
+                if (p.flags & 2) continue;
                 if (s % RT_GROUP == 0) ptx::mbar_wait(empty(s / RT_GROUP), par ^ 1);
                 ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
                 ptx::tma_load_2d(sbase + ring_off + s * stage_bytes, &tma_w1, full(s), c * 32, t * p.Cmid);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         if (lane == 0) {
             const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cmid);
             const uint32_t idesc2 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.C);
@@ -127,7 +150,9 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
                 const int hb = c % RT_HALO_BUFS;
                 if (t == 0) ptx::mbar_wait(hfull(hb), (uint32_t)((c / RT_HALO_BUFS) & 1));
-                ptx::mbar_wait(full(s), par);
+                if (!(p.flags & 2)) ptx::mbar_wait(full(s), par);
+                if (i == 0) trace_mark(2);             // first halo chunk + first W1 tile landed
+                if (t == 0 && c > 0) trace_mark(2 + c);  // chunk c available
                 ptx::tc_fence_after();
                 // tap (dy,dx) = the halo tile read (dy+1) padded rows and (dx+1) pixels further in;
                 // 8-pixel groups stay one padded row (RT_WP*128 B) apart.  base_offset stays 0: the
@@ -135,13 +160,14 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 const uint32_t a = sbase + hb * halo_bytes + (uint32_t)(((dy + 1) * p.BN * RT_WP + (dx + 1)) * 128);
                 const uint32_t b = sbase + ring_off + s * stage_bytes;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < ((p.flags & 1) ? 0 : 4); ++kk)
                     ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128_sbo(a + kk * 32, RT_WP * 128),
                                   ptx::smem_desc_sw128(b + kk * 32), idesc1, (i > 0 || kk > 0) ? 1u : 0u);
-                if (s % RT_GROUP == RT_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(empty(s / RT_GROUP));
+                if (!(p.flags & 2) && (s % RT_GROUP == RT_GROUP - 1 || i == ksteps - 1)) ptx::tc_commit(empty(s / RT_GROUP));
                 if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
             }
             ptx::tc_commit(d1full);
+            trace_mark(8);                             // all GEMM1 MMAs issued
             // GEMM2 once the epilogue has written relu(D1) as the A2 operand
             ptx::mbar_wait(w2full, 0);
             ptx::mbar_wait(a2ready, 0);
@@ -153,14 +179,16 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                                   ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
                                   (a > 0 || kk > 0) ? 1u : 0u);
             ptx::tc_commit(d2full);
+            trace_mark(11);                            // GEMM2 issued
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         // ---- epilogue 1: relu(D1) -> A2 operand in shared memory ----
-        ptx::mbar_wait(d1full, 0);
+        ptx::mbar_wait_sleep(d1full, 0);
         ptx::tc_fence_after();
+        if (tid == 0) trace_mark(9);                 // GEMM1 complete (epilogue sees D1)
         for (int a = 0; a < matoms; ++a) {
             float v[32];
             ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
@@ -177,6 +205,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a2ready);
+        if (tid == 0) trace_mark(10);                // A2 written
 
         // ---- epilogue 2: D2 + skip -> ReLU -> NHWC store ----
         const int bw = row & 7, grp = row >> 3;             // row = (y * BN + bn) * 8 + x
@@ -184,8 +213,9 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
         const bool valid = gx < p.W && gy < p.H && n < p.B;
         const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.C;
-        ptx::mbar_wait(d2full, 0);
+        ptx::mbar_wait_sleep(d2full, 0, 64);
         ptx::tc_fence_after();
+        if (tid == 0) trace_mark(12);                // GEMM2 complete
         for (int c0 = 0; c0 < p.C; c0 += 32) {
             float v[32];
             ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
@@ -203,9 +233,11 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             }
         }
     }
+    if (tid == 0) trace_mark(13);                    // epilogue 2 stores issued
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+    if (warp == 6) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+    if (tid == 128) trace_mark(14);                      // exit
 }
 
 int rt_pow2_ceil(int x) {
@@ -226,6 +258,10 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
                   int Cmid, int relu_out, cudaStream_t s) {
     if (!res_tc_supported(C, Cmid, r, out)) return VQB_ERR_UNSUPPORTED;
     ResTcParams q;
+    {
+        const char *fl = getenv("VQB_RES_FLAGS");
+        q.flags = fl ? atoi(fl) : 0;
+    }
     q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
     q.BH = rt_pow2_ceil(H) < 16 ? rt_pow2_ceil(H) : 16;
     q.BN = 16 / q.BH;
