@@ -13,6 +13,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One leader lane of a fully converged warp.  The single-thread issuers (TMA, tcgen05.mma/commit)
+// run their loops with ALL lanes converged and guard only the issuing instruction with this
+// predicate: inside an `if (lane == 0)` region the compiler wraps every UTCHMMA in an
+// ELECT/branch sequence (~14 SASS instructions, ~100 cycles per MMA, profiles/r01_mma_issue_*),
+// in converged code the UTCHMMAs issue back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -145,6 +156,25 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// The issue loops of the conv kernels are bound by the scalar instructions around each MMA
+// (profiles/r01_res_tc_timeline.txt), so they keep descriptors as running 32-bit words: lo = smem
+// address >> 4 (advance by +2 per 32-byte K slice), hi = constant per operand layout.
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+    return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);      // SBO, version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+}
+__device__ __forceinline__ void mma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // TMEM -> registers: this thread's lane (= accumulator row), 32 consecutive columns.

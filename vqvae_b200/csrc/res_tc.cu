@@ -48,12 +48,15 @@ struct ResTcParams {
     int BH, BN, tiles_x, tiles_y;          // tile = 8 px wide x (BH rows x BN images = 16)
     int stages;
     int relu_out;
+    int staged;             // 1: all halo chunks resident (skip read from smem) and the output tile is
+                            //    staged in smem (ring + A2 + W2 region) and TMA-stored
     int flags;              // perf experiments (env VQB_RES_FLAGS): 1 = skip GEMM1 MMAs, 2 = skip W1 loads/waits
 };
 
 __global__ void __launch_bounds__(RT_THREADS)
 res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w1,
-              const __grid_constant__ CUtensorMap tma_w2, const ResTcParams p) {
+              const __grid_constant__ CUtensorMap tma_w2, const __grid_constant__ CUtensorMap tma_out,
+              const ResTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -64,7 +67,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const int halo_bytes = (p.BH + 2) * p.BN * RT_WP * 128; // per 32-channel chunk
     const int stage_bytes = p.Cmid * 128;                   // W1 tile of one (tap, chunk)
     const int matoms = p.Cmid / 32;                         // 128-byte atoms of the GEMM2 K dimension
-    const int hbufs = chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS;
+    const int hbufs = (p.staged || chunks < RT_HALO_BUFS) ? chunks : RT_HALO_BUFS;
     const uint32_t ring_off = (uint32_t)(hbufs * halo_bytes);
     const uint32_t a2_off = ring_off + (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
     const uint32_t w2_off = a2_off + (uint32_t)(matoms * RT_A_BYTES);   // W2: matoms x [C rows][128 B]
@@ -77,8 +80,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const uint32_t a2ready = bars + 8u * (2 * RT_MAX_STAGES + 2);
     const uint32_t d2full = bars + 8u * (2 * RT_MAX_STAGES + 3);
     auto hfull = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + b); };
-    auto hempty = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + RT_HALO_BUFS + b); };
-    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_HALO_BUFS);
+    auto hempty = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS + b); };
+    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + RT_MISC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,7 +104,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_init(d1full, 1);
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
-        for (int b = 0; b < RT_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
+        for (int b = 0; b < hbufs; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
+        ptx::prefetch_tmap(&tma_out);
         ptx::fence_mbar_init();
     }
     if (warp == 6) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
@@ -111,63 +115,85 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const uint32_t tmem_base = *tmem_holder;
     if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
-    const int ksteps = 9 * chunks;             // chunk-major: the first MMAs need only halo chunk 0
 
     // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 MMA issuer, 6 TMEM
     // allocator.  The single-thread issuers get the HIGHER warp ids of their sub-partitions on purpose:
     // the scheduler favours high warp ids, and the epilogue warps poll barriers for most of the kernel.
     if (warp == 4) {
-        if (lane == 0) {
+        {
+            const bool leader = ptx::elect_one();       // converged warp, one issuing lane
             auto load_halo = [&](int c) {               // input tile + halo of one 32-channel chunk
-                const int b = c % RT_HALO_BUFS;
-                if (c >= RT_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / RT_HALO_BUFS) - 1) & 1));
-                ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
-                ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+                const int b = c % hbufs;
+                if (c >= hbufs) ptx::mbar_wait(hempty(b), (uint32_t)(((c / hbufs) - 1) & 1));
+                if (leader) {
+                    ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
+                    ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+                }
             };
             for (int c = 0; c < hbufs; ++c) load_halo(c);
-            ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
-            for (int a = 0; a < matoms; ++a)
-                ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
-            for (int i = 0; i < ksteps; ++i) {          // W1 tiles stream through the ring
-                const int s = i % S;
-                const uint32_t par = (uint32_t)((i / S) & 1);
-                const int c = i / 9, t = i - c * 9;
-                if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= RT_HALO_BUFS) load_halo(c + 1);
-                if (p.flags & 2) continue;
-                if (s % RT_GROUP == 0) ptx::mbar_wait(empty(s / RT_GROUP), par ^ 1);
-                ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
-                ptx::tma_load_2d(sbase + ring_off + s * stage_bytes, &tma_w1, full(s), c * 32, t * p.Cmid);
+            if (leader) {
+                ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
+                for (int a = 0; a < matoms; ++a)
+                    ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
+            }
+            // W1 tiles stream through the ring; running pointers, no div/mod in the loop
+            uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES;
+            uint32_t dst = sbase + ring_off;
+            for (int c = 0; c < chunks; ++c) {
+                if (c >= 1 && c + 1 < chunks && c + 1 >= hbufs) load_halo(c + 1);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if ((st & (RT_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
+                    if (leader) {
+                        ptx::mbar_expect_tx(full_bar, (uint32_t)stage_bytes);
+                        ptx::tma_load_2d(dst, &tma_w1, full_bar, c * 32, t * p.Cmid);
+                    }
+                    ++st; full_bar += 8; dst += (uint32_t)stage_bytes;
+                    if ((st & (RT_GROUP - 1)) == 0) empty_bar += 8;
+                    if (st == (uint32_t)S) {
+                        st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * RT_MAX_STAGES; dst = sbase + ring_off;
+                    }
+                }
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {
+            const bool leader = ptx::elect_one();       // all 32 lanes run the loop; only `leader` issues
             const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cmid);
             const uint32_t idesc2 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.C);
-            for (int i = 0; i < ksteps; ++i) {
-                const int s = i % S;
-                const uint32_t par = (uint32_t)((i / S) & 1);
-                const int c = i / 9, t = i - c * 9;
-                const int dy = t / 3 - 1, dx = t % 3 - 1;   // 3x3, pad 1
-                const int hb = c % RT_HALO_BUFS;
-                if (t == 0) ptx::mbar_wait(hfull(hb), (uint32_t)((c / RT_HALO_BUFS) & 1));
-                if (!(p.flags & 2)) ptx::mbar_wait(full(s), par);
-                if (i == 0) trace_mark(2);             // first halo chunk + first W1 tile landed
-                if (t == 0 && c > 0) trace_mark(2 + c);  // chunk c available
-                ptx::tc_fence_after();
-                // tap (dy,dx) = the halo tile read (dy+1) padded rows and (dx+1) pixels further in;
-                // 8-pixel groups stay one padded row (RT_WP*128 B) apart.  base_offset stays 0: the
-                // tensor core derives the swizzle phase from the absolute shared-memory address.
-                const uint32_t a = sbase + hb * halo_bytes + (uint32_t)(((dy + 1) * p.BN * RT_WP + (dx + 1)) * 128);
-                const uint32_t b = sbase + ring_off + s * stage_bytes;
+            // GEMM1 issue loop: running stage pointer / parity, taps unrolled (descriptor words are
+            // constants + one add), one commit per RT_GROUP stages.
+            const uint32_t a_hi = ptx::desc_hi_sw128(RT_WP * 128), b_hi = ptx::desc_hi_sw128(1024);
+            const uint32_t rs16 = (uint32_t)(p.BN * RT_WP * 128) >> 4;      // one padded halo row, in 16-byte units
+            const uint32_t b_lo0 = (sbase + ring_off) >> 4, b_step = (uint32_t)stage_bytes >> 4;
+            uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES, b_lo = b_lo0, acc = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int hb = c % hbufs;
+                ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
+                if (leader) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
+                const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
 #pragma unroll
-                for (int kk = 0; kk < ((p.flags & 1) ? 0 : 4); ++kk)
-                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128_sbo(a + kk * 32, RT_WP * 128),
-                                  ptx::smem_desc_sw128(b + kk * 32), idesc1, (i > 0 || kk > 0) ? 1u : 0u);
-                if (!(p.flags & 2) && (s % RT_GROUP == RT_GROUP - 1 || i == ksteps - 1)) ptx::tc_commit(empty(s / RT_GROUP));
-                if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
+                for (int t = 0; t < 9; ++t) {
+                    ptx::mbar_wait(full_bar, par);
+                    ptx::tc_fence_after();
+                    // tap (dy,dx) = (t/3-1, t%3-1): the halo tile read (dy+1) padded rows and (dx+1) pixels
+                    // further in; base_offset stays 0 (the swizzle phase comes from the absolute address)
+                    const uint32_t a_lo = h_lo + (uint32_t)(t / 3) * rs16 + (uint32_t)(t % 3) * 8u;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc1, acc);
+                        acc = 1;
+                    }
+                    ++st; full_bar += 8; b_lo += b_step;
+                    if ((st & (RT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
+                    if (st == (uint32_t)S) {
+                        st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * RT_MAX_STAGES; b_lo = b_lo0;
+                    }
+                }
+                if (leader) ptx::tc_commit(hempty(hb));     // chunk done: its halo buffer may be refilled
+                __syncwarp();
             }
-            ptx::tc_commit(d1full);
-            trace_mark(8);                             // all GEMM1 MMAs issued
+            if (leader) { ptx::tc_commit(d1full); trace_mark(8); }    // all GEMM1 MMAs issued
             // GEMM2 once the epilogue has written relu(D1) as the A2 operand
             ptx::mbar_wait(w2full, 0);
             ptx::mbar_wait(a2ready, 0);
@@ -175,11 +201,11 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             for (int a = 0; a < matoms; ++a)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
-                                  ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
-                                  (a > 0 || kk > 0) ? 1u : 0u);
-            ptx::tc_commit(d2full);
-            trace_mark(11);                            // GEMM2 issued
+                    if (leader)
+                        ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
+                                      ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
+                                      (a > 0 || kk > 0) ? 1u : 0u);
+            if (leader) { ptx::tc_commit(d2full); trace_mark(11); }   // GEMM2 issued
         }
     } else if (warp < 4) {
         const int q = warp & 3;
@@ -216,6 +242,38 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_wait_sleep(d2full, 0, 64);
         ptx::tc_fence_after();
         if (tid == 0) trace_mark(12);                // GEMM2 complete
+        if (p.staged) {
+            // skip = centre tap of the resident halo tiles; output tile staged in shared memory (over the
+            // W1 ring + A2 + W2, all dead once GEMM2 has completed) in MMA row order and TMA-stored:
+            // no global skip loads, no scattered 16-byte stores.
+            const int hrow = ((bh + 1) * p.BN + bn) * RT_WP + bw + 1;
+            for (int c0 = 0; c0 < p.C; c0 += 32) {
+                float v[32];
+                ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
+                ptx::tmem_ld_wait32(v);
+                const unsigned char *srow = sm + (c0 >> 5) * halo_bytes + hrow * 128;
+                unsigned char *orow = sm + ring_off + (c0 >> 5) * RT_A_BYTES + row * 128;
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const float4 sk = *reinterpret_cast<const float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
+                    float4 o = make_float4(v[c16 * 4] + sk.x, v[c16 * 4 + 1] + sk.y, v[c16 * 4 + 2] + sk.z, v[c16 * 4 + 3] + sk.w);
+                    if (p.relu_out) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4 *>(orow + ((c16 ^ (row & 7)) << 4)) = o;
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(1, 128);                       // the four epilogue warps
+            if (tid == 0) {
+                for (int a = 0; a < p.C / 32; ++a)               // box {32 ch, 8 px, BN img, BH rows}; OOB rows are clipped
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+                                     "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + ring_off + a * RT_A_BYTES),
+                                     "r"(a * 32), "r"(gx0), "r"(n0), "r"(gy0) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else
         for (int c0 = 0; c0 < p.C; c0 += 32) {
             float v[32];
             ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
@@ -269,7 +327,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     q.tiles_y = (H + q.BH - 1) / q.BH;
     const int tiles_n = (B + q.BN - 1) / q.BN;
 
-    CUtensorMap tin, tw1, tw2;
+    CUtensorMap tin, tw1, tw2, tout;
     // dims ordered (c, w, n, h): the BN images of a tile interleave row by row in shared memory
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)B, (uint64_t)H};
     const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)H * W * C * 4, (uint64_t)W * C * 4};
@@ -278,6 +336,12 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, r, dims, strides, box, es,
                                 CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    {
+        const uint32_t obox[4] = {32u, 8u, (uint32_t)q.BN, (uint32_t)q.BH};
+        rc = vqb_encode_tmap_4d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, dims, strides, obox, es,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     rc = vqb_encode_tmap_2d(&tw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, w1_tc, (uint64_t)C, (uint64_t)9 * Cmid,
                             (uint64_t)C * 4, 32, (uint32_t)Cmid, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -287,14 +351,31 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
 
     const int stage_bytes = Cmid * 128;
     const int chunks = C / 32;
-    const int hbufs = chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS;
-    const int fixed = hbufs * (q.BH + 2) * q.BN * RT_WP * 128 + (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128 +
-                      8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_HALO_BUFS) + 16 + 1024;
-    int stages = (226 * 1024 - fixed) / stage_bytes;
-    if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
-    if (stages >= 9 * chunks) stages = 9 * chunks;
-    else stages -= stages % RT_GROUP;             // a reused ring must hold whole commit groups
-    if (stages < RT_GROUP) return VQB_ERR_UNSUPPORTED;
+    const int halo_b = (q.BH + 2) * q.BN * RT_WP * 128;
+    const int tail = (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128;            // A2 + W2
+    const int misc = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS) + 16 + 1024;
+    // staged mode: every halo chunk resident + a ring that, together with A2 + W2, holds the 128 x C output tile
+    int stages = 0;
+    q.staged = 0;
+    {
+        int need = 128 * C * 4 - tail;                       // ring bytes needed for the output staging
+        int st = (need + stage_bytes - 1) / stage_bytes;
+        if (st < RT_GROUP) st = RT_GROUP;
+        st = (st + RT_GROUP - 1) / RT_GROUP * RT_GROUP;
+        if (st <= RT_MAX_STAGES && chunks * halo_b + st * stage_bytes + tail + misc <= 227 * 1024 && chunks <= RT_MAX_CHUNKS) {
+            q.staged = 1;
+            stages = st;
+        }
+    }
+    const int hbufs = q.staged ? chunks : (chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS);
+    const int fixed = hbufs * halo_b + tail + misc;
+    if (!q.staged) {
+        stages = (226 * 1024 - fixed) / stage_bytes;
+        if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
+        if (stages >= 9 * chunks) stages = 9 * chunks;
+        else stages -= stages % RT_GROUP;             // a reused ring must hold whole commit groups
+        if (stages < RT_GROUP) return VQB_ERR_UNSUPPORTED;
+    }
     q.stages = stages;
     const int smem = stages * stage_bytes + fixed;
     static int attr_max = 0;
@@ -305,7 +386,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     }
     const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
     if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
-    res_tc_kernel<<<(unsigned)grid, RT_THREADS, smem, s>>>(tin, tw1, tw2, q);
+    res_tc_kernel<<<(unsigned)grid, RT_THREADS, smem, s>>>(tin, tw1, tw2, tout, q);
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
