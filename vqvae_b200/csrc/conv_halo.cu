@@ -101,50 +101,67 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    const int ksteps = 9 * chunks;             // k-step i: chunk-major so the first MMAs need only chunk 0
+    // Issuer warps run fully converged; only the elected leader lane issues TMA / MMA / commits, and
+    // every per-k-step quantity is a running pointer (profiles/r01_res_tc_timeline.txt: the issue loops
+    // are bound by their own scalar instructions, not by TMA or the tensor pipe).
     if (warp == 0) {
-        if (lane == 0) {
-            auto load_halo = [&](int c) {
-                const int b = c % CH_HALO_BUFS;
-                if (c >= CH_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / CH_HALO_BUFS) - 1) & 1));
+        const bool leader = ptx::elect_one();
+        auto load_halo = [&](int c) {
+            const int b = c % CH_HALO_BUFS;
+            if (c >= CH_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / CH_HALO_BUFS) - 1) & 1));
+            if (leader) {
                 ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
                 ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
-            };
-            for (int c = 0; c < hbufs; ++c) load_halo(c);
-            for (int i = 0; i < ksteps; ++i) {
-                const int s = i % S;
-                const uint32_t par = (uint32_t)((i / S) & 1);
-                const int c = i / 9, t = i - c * 9;
-                // refill the halo buffer chunk c-1 just vacated with chunk c+1 (the ring keeps the MMAs fed)
-                if (t == 0 && c >= 1 && c + 1 < chunks && c + 1 >= CH_HALO_BUFS) load_halo(c + 1);
-                if (s % CH_GROUP == 0) ptx::mbar_wait(bempty(s / CH_GROUP), par ^ 1);
-                ptx::mbar_expect_tx(bfull(s), (uint32_t)b_bytes);
-                ptx::tma_load_2d(sbase + ring_off + s * b_bytes, &tma_w, bfull(s), c * 32, p.tap_w[t] * p.Cout);
+            }
+        };
+        for (int c = 0; c < hbufs; ++c) load_halo(c);
+        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CH_MAX_STAGES, dst = sbase + ring_off;
+        for (int c = 0; c < chunks; ++c) {
+            // refill the halo buffer chunk c-1 just vacated with chunk c+1 (the ring keeps the MMAs fed)
+            if (c >= 1 && c + 1 < chunks && c + 1 >= CH_HALO_BUFS) load_halo(c + 1);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if ((st & (CH_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
+                if (leader) {
+                    ptx::mbar_expect_tx(full_bar, (uint32_t)b_bytes);
+                    ptx::tma_load_2d(dst, &tma_w, full_bar, c * 32, p.tap_w[t] * p.Cout);
+                }
+                ++st; full_bar += 8; dst += (uint32_t)b_bytes;
+                if ((st & (CH_GROUP - 1)) == 0) empty_bar += 8;
+                if (st == (uint32_t)S) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CH_MAX_STAGES; dst = sbase + ring_off; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
-            for (int i = 0; i < ksteps; ++i) {
-                const int s = i % S;
-                const uint32_t par = (uint32_t)((i / S) & 1);
-                const int c = i / 9, t = i - c * 9;
-                const int hb = c % CH_HALO_BUFS;
-                if (t == 0) ptx::mbar_wait(hfull(hb), (uint32_t)((c / CH_HALO_BUFS) & 1));
-                ptx::mbar_wait(bfull(s), par);
-                ptx::tc_fence_after();
-                const uint32_t a = sbase + hb * halo_bytes +
-                                   (uint32_t)(((p.tap_dy[t] + 1) * p.BN * WP + (p.tap_dx[t] + 1)) * 128);
-                const uint32_t b = sbase + ring_off + s * b_bytes;
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
+        const uint32_t a_hi = ptx::desc_hi_sw128(WP * 128), b_hi = ptx::desc_hi_sw128(1024);
+        const uint32_t rs16 = (uint32_t)(p.BN * WP * 128) >> 4;        // one padded halo row in 16-byte units
+        const uint32_t b_lo0 = (sbase + ring_off) >> 4, b_step = (uint32_t)b_bytes >> 4;
+        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CH_MAX_STAGES, b_lo = b_lo0, acc = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int hb = c % CH_HALO_BUFS;
+            ptx::mbar_wait(hfull(hb), (uint32_t)((c / CH_HALO_BUFS) & 1));
+            const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    ptx::mma_tf32(tmem_base, halo_desc(a + kk * 32, p.bo_mode), ptx::smem_desc_sw128(b + kk * 32), idesc,
-                                  (i > 0 || kk > 0) ? 1u : 0u);
-                if (s % CH_GROUP == CH_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(bempty(s / CH_GROUP));
-                if (t == 8) ptx::tc_commit(hempty(hb));        // chunk done: its halo buffer may be refilled
+            for (int t = 0; t < 9; ++t) {
+                ptx::mbar_wait(full_bar, par);
+                ptx::tc_fence_after();
+                // tap (dy,dx): the halo tile read (dy+1) padded rows and (dx+1) pixels further in; the
+                // descriptor's base_offset stays 0 (swizzle phase = absolute address bits, measured)
+                const uint32_t a_lo = h_lo + (uint32_t)(p.tap_dy[t] + 1) * rs16 + (uint32_t)(p.tap_dx[t] + 1) * 8u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, acc);
+                    acc = 1;
+                }
+                ++st; full_bar += 8; b_lo += b_step;
+                if ((st & (CH_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
+                if (st == (uint32_t)S) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CH_MAX_STAGES; b_lo = b_lo0; }
             }
-            ptx::tc_commit(tfull);
+            if (leader) ptx::tc_commit(hempty(hb));            // chunk done: its halo buffer may be refilled
+            __syncwarp();
         }
+        if (leader) ptx::tc_commit(tfull);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;                 // = (y * BN + bn) * 8 + x

@@ -88,37 +88,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
     const int kchunks = p.Cin / 32;
     const int ksteps = p.ntaps[ph] * kchunks;
 
+    // Issuer warps run fully converged; only the elected leader lane issues TMA / MMA / commits and every
+    // per-k-step quantity is a running pointer (profiles/r01_res_tc_timeline.txt).
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < ksteps; ++i) {
-                const int s = i % CT_STAGES;
-                const uint32_t par = (uint32_t)((i / CT_STAGES) & 1);
-                const int t = i / kchunks, cc = i - t * kchunks;
-                if (s % CT_GROUP == 0) ptx::mbar_wait(empty(s / CT_GROUP), par ^ 1);
-                ptx::mbar_expect_tx(full(s), (uint32_t)stage_bytes);
-                const uint32_t dst = sbase + s * stage_bytes;
-                ptx::tma_load_4d(dst, &tma_in, full(s), cc * 32, gx0 * p.in_step + p.tap_dx[ph][t],
-                                 gy0 * p.in_step + p.tap_dy[ph][t], n0);
-                ptx::tma_load_2d(dst + A_BYTES, &tma_w, full(s), cc * 32, p.tap_w[ph][t] * p.Cout);
+        const bool leader = ptx::elect_one();
+        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CT_MAX_STAGES, dst = sbase;
+        const int ix0 = gx0 * p.in_step, iy0 = gy0 * p.in_step;
+        for (int t = 0; t < p.ntaps[ph]; ++t) {
+            const int cx = ix0 + p.tap_dx[ph][t], cy = iy0 + p.tap_dy[ph][t], wrow = p.tap_w[ph][t] * p.Cout;
+            for (int cc = 0; cc < kchunks; ++cc) {
+                if ((st & (CT_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
+                if (leader) {
+                    ptx::mbar_expect_tx(full_bar, (uint32_t)stage_bytes);
+                    ptx::tma_load_4d(dst, &tma_in, full_bar, cc * 32, cx, cy, n0);
+                    ptx::tma_load_2d(dst + A_BYTES, &tma_w, full_bar, cc * 32, wrow);
+                }
+                ++st; full_bar += 8; dst += (uint32_t)stage_bytes;
+                if ((st & (CT_GROUP - 1)) == 0) empty_bar += 8;
+                if (st == (uint32_t)CT_STAGES) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CT_MAX_STAGES; dst = sbase; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
-            for (int i = 0; i < ksteps; ++i) {
-                const int s = i % CT_STAGES;
-                const uint32_t par = (uint32_t)((i / CT_STAGES) & 1);
-                ptx::mbar_wait(full(s), par);
-                ptx::tc_fence_after();
-                const uint32_t a = sbase + s * stage_bytes, b = a + A_BYTES;
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
+        const uint32_t d_hi = ptx::desc_hi_sw128(1024);
+        const uint32_t a_lo0 = sbase >> 4, step16 = (uint32_t)stage_bytes >> 4;
+        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CT_MAX_STAGES, a_lo = a_lo0, acc = 0;
+        for (int i = 0; i < ksteps; ++i) {
+            ptx::mbar_wait(full_bar, par);
+            ptx::tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    ptx::mma_tf32(tmem_base, ptx::smem_desc_sw128(a + kk * 32), ptx::smem_desc_sw128(b + kk * 32),
-                                  idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (s % CT_GROUP == CT_GROUP - 1 || i == ksteps - 1) ptx::tc_commit(empty(s / CT_GROUP));
+            for (int kk = 0; kk < 4; ++kk) {
+                if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, d_hi, a_lo + (A_BYTES >> 4) + 2u * kk, d_hi, idesc, acc);
+                acc = 1;
             }
-            ptx::tc_commit(tfull);
+            ++st; full_bar += 8; a_lo += step16;
+            if ((st & (CT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
+            if (st == (uint32_t)CT_STAGES) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CT_MAX_STAGES; a_lo = a_lo0; }
         }
+        if (leader) ptx::tc_commit(tfull);
+        __syncwarp();
     } else if (warp >= 4) {
         // ---- epilogue: this thread owns output pixel `row` of the tile ----
         const int q = warp & 3;

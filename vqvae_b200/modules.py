@@ -52,19 +52,17 @@ def precision(name: str):
 
 
 class _PackedWeights:
-    """Cache of tap-major packed conv weights, refreshed when a parameter changes
-    (load_state_dict / .to() / in-place edits bump ``_version`` or move the storage)."""
-
-    def __init__(self):
-        self._cache = {}
+    """Tap-major packed conv weights, cached ON the parameter object (so the cache dies with it:
+    a dict keyed by id(param) can hand a new model the stale packing of a freed one) and refreshed
+    when the parameter changes (load_state_dict / .to() / in-place edits bump ``_version`` or move
+    the storage)."""
 
     def get(self, param, transposed):
-        key = id(param)
-        tag = (param._version, param.data_ptr(), str(param.device))
-        hit = self._cache.get(key)
+        tag = (param._version, param.data_ptr(), str(param.device), bool(transposed))
+        hit = getattr(param, "_vqb_packed", None)
         if hit is None or hit[0] != tag:
             hit = (tag, ops.pack_conv_weight(param, transposed))
-            self._cache[key] = hit
+            param._vqb_packed = hit
         return hit[1]
 
 
