@@ -238,7 +238,16 @@ int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_t
     const int stage_bytes = A_BYTES + p.Cout * 128;
     int maxk = 1;
     for (int i = 0; i < nph; ++i) if (q.ntaps[i] * (p.Cin / 32) > maxk) maxk = q.ntaps[i] * (p.Cin / 32);
-    int stages = (200 * 1024) / stage_bytes;      // deep ring: the k-loop is TMA-latency bound
+    int stages = (200 * 1024) / stage_bytes;
+    {
+        // more CTAs than one wave of 1-CTA/SM residency (e.g. the 4 phases of a stride-2 transposed conv):
+        // keep the ring small enough for 2 CTAs per SM instead of running 2x the waves
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long ctas = (long long)q.tiles_x * q.tiles_y * tiles_n * nph;
+        if (ctas > sms && stages > (108 * 1024) / stage_bytes) stages = (108 * 1024) / stage_bytes;
+    }
     if (stages > CT_MAX_STAGES) stages = CT_MAX_STAGES;
     if (stages > maxk) stages = maxk;
     else stages -= stages % CT_GROUP;             // a reused ring must hold whole commit groups

@@ -189,13 +189,16 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             bulk_wait_all0();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, elected leader lane issues) =====================
+        {
+            const bool leader = ptx::elect_one();
             constexpr uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, TM, CN);
+            const uint32_t d_hi = ptx::desc_hi_sw128(1024);
             int it = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int zs = it & 1;
                 ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+                const uint32_t za_lo = (sbase + OFF_Z + zs * ZSTAGE) >> 4;
                 for (int c = 0; c < nchunks; ++c) {
                     const long long gc = (long long)it * nchunks + c;
                     int es;
@@ -209,15 +212,17 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     const int ab = (int)(gc & 1);
                     ptx::mbar_wait(bar(T_EMPTY + ab), (uint32_t)(((gc >> 1) & 1) ^ 1));
                     ptx::tc_fence_after();
-                    const uint32_t za = sbase + OFF_Z + zs * ZSTAGE, ea = sbase + OFF_E + es * ESTAGE;
+                    const uint32_t ea_lo = (sbase + OFF_E + es * ESTAGE) >> 4;
 #pragma unroll
-                    for (int ks = 0; ks < DD / 8; ++ks) {
-                        const uint64_t ad = ptx::smem_desc_sw128(za + (ks >> 2) * ZATOM + (ks & 3) * 32);
-                        const uint64_t bd = ptx::smem_desc_sw128(ea + (ks >> 2) * EATOM + (ks & 3) * 32);
-                        ptx::mma_tf32(tmem_base + ab * CN, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                    for (int ks = 0; ks < DD / 8; ++ks)
+                        if (leader)
+                            ptx::mma_tf32_w(tmem_base + ab * CN, za_lo + (ks >> 2) * (ZATOM >> 4) + (ks & 3) * 2, d_hi,
+                                            ea_lo + (ks >> 2) * (EATOM >> 4) + (ks & 3) * 2, d_hi, idesc, ks > 0 ? 1u : 0u);
+                    if (leader) {
+                        ptx::tc_commit(bar(T_FULL + ab));
+                        if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
                     }
-                    ptx::tc_commit(bar(T_FULL + ab));
-                    if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
+                    __syncwarp();
                 }
             }
         }
