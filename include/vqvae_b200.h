@@ -151,6 +151,9 @@ int vqb_relu_f32(float *x, int64_t n, void *stream);
 /* Diagnostic: copy the first n (<= 32) entries of the in-kernel timeline (globaltimer ns of CTA 0
  * of the last fused residual kernel) to host memory.  Synchronises the device.          */
 int vqb_debug_read_trace(unsigned long long *dst, int n);
+/* Same for the tcgen05 VQ kernel (epilogue warp 4 of CTA 0, local tiles 1-2, 16 marks each; enabled with
+ * the environment variable VQB_TC_FLAGS=8).                                                              */
+int vqb_debug_read_trace_vq(unsigned long long *dst, int n);
 
 /* ---- layout changes at the module boundary (quantizer.py:45, :74) ---------------- */
 int vqb_nchw_to_nhwc_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);

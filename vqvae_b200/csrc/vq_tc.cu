@@ -33,7 +33,22 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+__device__ unsigned long long g_vqb_trace_vq[64];            // diagnostic timeline (vqb_debug_read_trace_vq)
+extern "C" int vqb_debug_read_trace_vq(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 64) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_vqb_trace_vq, sizeof(unsigned long long) * n));
+}
+
 namespace {
+
+// timeline of epilogue warp 4 / CTA 0 for local tiles 1 and 2 (16 marks each), globaltimer ns
+__device__ __forceinline__ void vq_mark(bool on, int it, int i) {
+    if (on && it >= 1 && it <= 2) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_vqb_trace_vq[(it - 1) * 16 + i] = t;
+    }
+}
 
 constexpr int TM = 128;          // latent rows per tile (UMMA M)
 constexpr int CN = 256;          // codes per chunk (UMMA N)
@@ -295,7 +310,10 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
             unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
+            const bool tr = kDebug == false && (p.flags & 8) && blockIdx.x == 0 && tid == 128;
+            vq_mark(tr, it, 0);
             ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            vq_mark(tr, it, 1);
 
             // ---- A_i = sum_d fl(z^2), canonical left-to-right order (quantizer.py:49) ----
             float A = 0.f;
@@ -321,8 +339,10 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 const long long gc = (long long)it * nchunks + c;
                 const int ab = (int)(gc & 1);
                 const int es = resident ? c : (int)(gc & 1);
+                vq_mark(tr, it, 2 + 2 * (c & 1));
                 ptx::mbar_wait(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1));
                 ptx::tc_fence_after();
+                vq_mark(tr, it, 3 + 2 * (c & 1));
                 const float *bch = bsm + es * CN + h * 128;
                 const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
                 const int gbase = (c * CN + h * 128) / 8;
@@ -374,6 +394,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 }
             }
 
+            vq_mark(tr, it, 6);
             // ---- approximate minimum of the whole row (both column halves) ----
             xmin[et] = run_min;
             ptx::named_bar_sync(1 + q, 64);
@@ -409,6 +430,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             }
             if (pnc < 0) slow_row = true;
 
+            vq_mark(tr, it, 7);
             // ---- z row -> registers (needed for the exact chains and for z_q) ----
             float zr[DD];
 #pragma unroll
@@ -420,6 +442,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                     zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
                 }
 
+            vq_mark(tr, it, 8);
             // ---- exact canonical re-scoring ----
             float bd = 0.f;
             int bk = -1;
@@ -491,6 +514,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 // non-finite data or overflowing lists (e.g. many duplicated codes): every code, exactly
                 for (int g = 0; g * 8 < p.K; ++g) rescore_group(g);
             }
+            vq_mark(tr, it, 9);
             xbd[et] = bd;
             xbk[et] = bk;
             ptx::named_bar_sync(1 + q, 64);
@@ -500,6 +524,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 if (ok >= 0 && (bk < 0 || vq_better(od, ok, bd, bk))) { bd = od; bk = ok; }
             }
 
+            vq_mark(tr, it, 10);
             // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram ----
             const long long grow = tile * TM + row;
             {
@@ -535,6 +560,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             ptx::fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(Q_FULL + zs));
+            vq_mark(tr, it, 11);
         }
 
         // ---- CTA reduction of the SSE partial, histogram flush ----
