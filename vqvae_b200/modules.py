@@ -244,10 +244,9 @@ class VectorQuantizer(nn.Module):
             w = w.float()
         return w if w.is_contiguous() else w.contiguous()
 
-    def _quantize_rows(self, rows, group=None):
-        """rows (N, e_dim) fp32 CUDA -> (loss, zq_rows, perplexity, idx (N,))."""
-        idx, zq, sse, hist = ops.vq_forward(rows, self._codebook())
-        n_total = rows.shape[0]
+    def _scalars(self, sse, hist, n_local, group=None):
+        """(loss, perplexity) from the VQ kernel's sufficient statistics (quantizer.py:63-64, :70-71)."""
+        n_total = n_local
         if group is not None and torch.distributed.get_world_size(group) > 1:
             # batch-sharded forward (SURVEY 8e): loss and perplexity are the only
             # cross-sample quantities; reduce their sufficient statistics.
@@ -255,7 +254,12 @@ class VectorQuantizer(nn.Module):
             # split), so the global row count is n_local * world_size: no host sync needed
             hist, sse = reduce_vq_stats(hist, sse, group)
             n_total = n_total * torch.distributed.get_world_size(group)
-        loss, perp = ops.vq_finish(sse, hist, n_total, self.n_e, self.e_dim, self.beta)
+        return ops.vq_finish(sse, hist, n_total, self.n_e, self.e_dim, self.beta)
+
+    def _quantize_rows(self, rows, group=None):
+        """rows (N, e_dim) fp32 CUDA -> (loss, zq_rows, perplexity, idx (N,))."""
+        idx, zq, sse, hist = ops.vq_forward(rows, self._codebook())
+        loss, perp = self._scalars(sse, hist, rows.shape[0], group)
         return loss, zq, perp, idx
 
     def forward(self, z):
@@ -295,6 +299,7 @@ class VQVAE(nn.Module):
         # batch-sharded inference: set to a torch.distributed process group so that
         # embedding_loss / perplexity equal the single-process values
         self.process_group = None
+        self._side_stream = None
         self.last_min_encoding_indices = None
 
     def _encode_rows(self, x):
@@ -309,9 +314,28 @@ class VQVAE(nn.Module):
         z_e, B, H, W = self._encode_rows(x)                                  # vqvae.py:31-33
         vq = self.vector_quantization
         D = vq.e_dim
-        embedding_loss, zq, perplexity, idx = vq._quantize_rows(z_e.view(-1, D), self.process_group)
+        group = self.process_group
+        if group is not None and torch.distributed.get_world_size(group) > 1:
+            # batch-sharded: the decoder does not depend on the two cross-sample scalars, so their tiny
+            # all-reduce + finisher run on a side stream and overlap the decoder; fork/join
+            # with events, so the whole forward stays capturable in one CUDA graph.
+            idx, zq, sse, hist = ops.vq_forward(z_e.view(-1, D), vq._codebook())
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                embedding_loss, perplexity = vq._scalars(sse, hist, z_e.shape[0] * H * W, group)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in (sse, hist, embedding_loss, perplexity):
+                        t.record_stream(side)
+            x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
+            main.wait_stream(side)
+        else:
+            embedding_loss, zq, perplexity, idx = vq._quantize_rows(z_e.view(-1, D))
+            x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
         self.last_min_encoding_indices = idx.view(-1, 1)
-        x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
         if verbose:                                                          # :38-42 (Q8)
             print('original data shape:', x.shape)
             print('encoded data shape:', torch.Size((B, D, H, W)))
