@@ -1,4 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/vqvae_b200.h.
+#include <cstdlib>
+
 #include "common.cuh"
 
 size_t vq_exact_workspace_bytes(int K);
@@ -27,6 +29,15 @@ bool conv_halo_supported(const ConvLaunch &p);
 int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
 int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
+
+int vqb_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("VQB_PDL");
+        on = e ? (atoi(e) != 0) : 1;
+    }
+    return on;
+}
 
 unsigned long long g_vqb_launches = 0;
 static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel

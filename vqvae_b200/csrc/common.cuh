@@ -34,4 +34,26 @@ int launch_conv_small_cout(const ConvLaunch &p, cudaStream_t s);
 extern unsigned long long g_vqb_launches;
 #define VQB_COUNT_LAUNCH(n) (g_vqb_launches += (n))
 
+// Programmatic dependent launch: the next kernel of the layer chain may start its prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) while this one drains; it blocks in pdl_wait() until the previous
+// grid has completed and its writes are visible.  VQB_PDL=0 in the environment disables the attribute.
+int vqb_pdl_enabled();
+#ifdef __CUDACC__
+#include <utility>
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vqb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = vqb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 static inline int vqb_cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

@@ -100,6 +100,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();       // the next layer may start its prologue
+    pdl_wait();                    // ... and this one waits here for the previous layer's output
 
     // Issuer warps run fully converged; only the elected leader lane issues TMA / MMA / commits, and
     // every per-k-step quantity is a running pointer (profiles/r01_res_tc_timeline.txt: the issue loops
@@ -294,7 +296,7 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     }
     const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
     if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
-    conv_halo_kernel<<<(unsigned)grid, CH_THREADS, smem, s>>>(tin, tw, q);
+    if (cudaError_t le = vqb_launch(conv_halo_kernel, dim3((unsigned)grid), dim3(CH_THREADS), (size_t)smem, s, tin, tw, q)) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -50,6 +50,8 @@ conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, con
         const int atom = k >> 5, kk = k & 31;
         *reinterpret_cast<float *>(sm + b_off + atom * b_atom + co * 128 + (((kk >> 2) ^ (co & 7)) << 4) + (kk & 3) * 4) = v;
     }
+    pdl_launch_dependents();
+    pdl_wait();                    // x may be written by the previous kernel / copy
     // ---- A operand: im2col of the tile, thread = (pixel row, K atom) ----
     {
         const int row = tid & 127, atom = tid >> 7;
@@ -142,7 +144,7 @@ int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float 
         if (e != cudaSuccess) return (int)e;
         attr_max = smem;
     }
-    conv_in_tc_kernel<<<(unsigned)blocks, CI_THREADS, smem, s>>>(x, wp, bias, y, B, H, W, Cout, relu);
+    if (cudaError_t le = vqb_launch(conv_in_tc_kernel, dim3((unsigned)blocks), dim3(CI_THREADS), (size_t)smem, s, x, wp, bias, y, B, H, W, Cout, relu)) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

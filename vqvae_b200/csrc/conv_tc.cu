@@ -84,6 +84,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();       // the next layer may start its prologue
+    pdl_wait();                    // ... and this one waits here for the previous layer's output
 
     const int kchunks = p.Cin / 32;
     const int ksteps = p.ntaps[ph] * kchunks;
@@ -262,7 +264,7 @@ int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_t
     }
     const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
     if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
-    conv_tc_kernel<<<dim3((unsigned)grid, (unsigned)nph), CT_THREADS, smem, s>>>(tin, tw, q);
+    if (cudaError_t le = vqb_launch(conv_tc_kernel, dim3((unsigned)grid, (unsigned)nph), dim3(CT_THREADS), (size_t)smem, s, tin, tw, q)) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -113,6 +113,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();       // the next layer may start its prologue
+    pdl_wait();                    // ... and this one waits here for the previous layer's output
     if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
 
@@ -386,7 +388,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     }
     const long long grid = (long long)q.tiles_x * q.tiles_y * tiles_n;
     if (grid <= 0 || grid > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
-    res_tc_kernel<<<(unsigned)grid, RT_THREADS, smem, s>>>(tin, tw1, tw2, tout, q);
+    if (cudaError_t le = vqb_launch(res_tc_kernel, dim3((unsigned)grid), dim3(RT_THREADS), (size_t)smem, s, tin, tw1, tw2, tout, q)) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

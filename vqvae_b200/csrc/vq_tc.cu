@@ -158,6 +158,8 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();
+    pdl_wait();                    // z_e is written by the previous layer
 
     if (warp == 0) {
         // ===================== TMA producer (+ z_q tile stores) =====================
@@ -667,7 +669,7 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
         p.flags = fl ? atoi(fl) : 0;
     }
     if (dbg) vq_tc_kernel<true><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
-    else vq_tc_kernel<false><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
+    else if (cudaError_t le = vqb_launch(vq_tc_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)) return (int)le;
     vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
     VQB_COUNT_LAUNCH(nlaunch);
     return vqb_cuda_status(cudaGetLastError());
