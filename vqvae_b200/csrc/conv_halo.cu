@@ -100,8 +100,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    pdl_launch_dependents();       // the next layer may start its prologue
-    pdl_wait();                    // ... and this one waits here for the previous layer's output
+    pdl_launch_dependents();       // the next layer may start its prologue (it blocks in its own pdl_wait)
 
     // Issuer warps run fully converged; only the elected leader lane issues TMA / MMA / commits, and
     // every per-k-step quantity is a running pointer (profiles/r01_res_tc_timeline.txt: the issue loops
@@ -116,17 +115,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                 ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
             }
         };
+        // weights do not depend on the previous layer: the first ring-full of weight tiles is requested
+        // BEFORE pdl_wait(), i.e. while the previous kernel is still draining
+        const int prefill = S < 9 * chunks ? S : 9 * chunks;
+        if (leader)
+            for (int i = 0; i < prefill; ++i) {
+                ptx::mbar_expect_tx(bars + 8u * i, (uint32_t)b_bytes);
+                ptx::tma_load_2d(sbase + ring_off + i * b_bytes, &tma_w, bars + 8u * i, (i / 9) * 32, p.tap_w[i % 9] * p.Cout);
+            }
+        pdl_wait();                                     // the input activation is the previous layer's output
         for (int c = 0; c < hbufs; ++c) load_halo(c);
         uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CH_MAX_STAGES, dst = sbase + ring_off;
+        int kidx = 0;
         for (int c = 0; c < chunks; ++c) {
             // refill the halo buffer chunk c-1 just vacated with chunk c+1 (the ring keeps the MMAs fed)
             if (c >= 1 && c + 1 < chunks && c + 1 >= CH_HALO_BUFS) load_halo(c + 1);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                if ((st & (CH_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
-                if (leader) {
-                    ptx::mbar_expect_tx(full_bar, (uint32_t)b_bytes);
-                    ptx::tma_load_2d(dst, &tma_w, full_bar, c * 32, p.tap_w[t] * p.Cout);
+            for (int t = 0; t < 9; ++t, ++kidx) {
+                if (kidx >= prefill) {
+                    if ((st & (CH_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
+                    if (leader) {
+                        ptx::mbar_expect_tx(full_bar, (uint32_t)b_bytes);
+                        ptx::tma_load_2d(dst, &tma_w, full_bar, c * 32, p.tap_w[t] * p.Cout);
+                    }
                 }
                 ++st; full_bar += 8; dst += (uint32_t)b_bytes;
                 if ((st & (CH_GROUP - 1)) == 0) empty_bar += 8;
@@ -172,6 +183,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
         const int gx = gx0 + x, gy = gy0 + yy, n = n0 + bn;
         const bool valid = gx < p.W && gy < p.H && n < p.B;
         const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.Cout;
+        pdl_wait();                                     // (skip, if any, is the previous layers' output)
         ptx::mbar_wait(tfull, 0);
         ptx::tc_fence_after();
         if (p.shuffle_cout > 0) {

@@ -113,8 +113,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    pdl_launch_dependents();       // the next layer may start its prologue
-    pdl_wait();                    // ... and this one waits here for the previous layer's output
+    pdl_launch_dependents();       // the next layer may start its prologue (it blocks in its own pdl_wait)
     if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
 
@@ -132,23 +131,35 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
                 }
             };
-            for (int c = 0; c < hbufs; ++c) load_halo(c);
+            // weights do not depend on the previous layer: W2 and the first ring-full of W1 tiles are
+            // requested BEFORE pdl_wait(), i.e. while the previous kernel is still draining
             if (leader) {
                 ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
                 for (int a = 0; a < matoms; ++a)
                     ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
             }
+            const int prefill = S < 9 * chunks ? S : 9 * chunks;
+            if (leader)
+                for (int i = 0; i < prefill; ++i) {
+                    ptx::mbar_expect_tx(bars + 8u * i, (uint32_t)stage_bytes);
+                    ptx::tma_load_2d(sbase + ring_off + i * stage_bytes, &tma_w1, bars + 8u * i, (i / 9) * 32, (i % 9) * p.Cmid);
+                }
+            pdl_wait();                                 // the input activation is the previous layer's output
+            for (int c = 0; c < hbufs; ++c) load_halo(c);
             // W1 tiles stream through the ring; running pointers, no div/mod in the loop
             uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES;
             uint32_t dst = sbase + ring_off;
+            int kidx = 0;
             for (int c = 0; c < chunks; ++c) {
                 if (c >= 1 && c + 1 < chunks && c + 1 >= hbufs) load_halo(c + 1);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    if ((st & (RT_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
-                    if (leader) {
-                        ptx::mbar_expect_tx(full_bar, (uint32_t)stage_bytes);
-                        ptx::tma_load_2d(dst, &tma_w1, full_bar, c * 32, t * p.Cmid);
+                for (int t = 0; t < 9; ++t, ++kidx) {
+                    if (kidx >= prefill) {
+                        if ((st & (RT_GROUP - 1)) == 0) ptx::mbar_wait(empty_bar, par ^ 1);
+                        if (leader) {
+                            ptx::mbar_expect_tx(full_bar, (uint32_t)stage_bytes);
+                            ptx::tma_load_2d(dst, &tma_w1, full_bar, c * 32, t * p.Cmid);
+                        }
                     }
                     ++st; full_bar += 8; dst += (uint32_t)stage_bytes;
                     if ((st & (RT_GROUP - 1)) == 0) empty_bar += 8;
@@ -213,6 +224,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        pdl_wait();     // (non-staged path reads the skip tensor from global memory)
         // ---- epilogue 1: relu(D1) -> A2 operand in shared memory ----
         ptx::mbar_wait_sleep(d1full, 0);
         ptx::tc_fence_after();
