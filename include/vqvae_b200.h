@@ -154,6 +154,8 @@ int vqb_debug_read_trace(unsigned long long *dst, int n);
 /* Same for the tcgen05 VQ kernel (epilogue warp 4 of CTA 0, local tiles 1-2, 16 marks each; enabled with
  * the environment variable VQB_TC_FLAGS=8).                                                              */
 int vqb_debug_read_trace_vq(unsigned long long *dst, int n);
+/* Per-CTA (start, end<<10 | smid) globaltimer pairs of the last traced tcgen05 VQ launch.               */
+int vqb_debug_read_cta_times(unsigned long long *dst, int n);
 
 /* ---- layout changes at the module boundary (quantizer.py:45, :74) ---------------- */
 int vqb_nchw_to_nhwc_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);

@@ -39,14 +39,22 @@ extern "C" int vqb_debug_read_trace_vq(unsigned long long *dst, int n) {
     return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_vqb_trace_vq, sizeof(unsigned long long) * n));
 }
 
+__device__ unsigned long long g_vqb_cta_t[512];              // per-CTA (start, end) globaltimer, flags & 8
+extern "C" int vqb_debug_read_cta_times(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 512) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_vqb_cta_t, sizeof(unsigned long long) * n));
+}
+
 namespace {
 
 // timeline of epilogue warp 4 / CTA 0 for local tiles 1 and 2 (16 marks each), globaltimer ns
+__device__ int g_vqb_trace_tile = 1;      // first of the two local tiles that are traced
 __device__ __forceinline__ void vq_mark(bool on, int it, int i) {
-    if (on && it >= 1 && it <= 2) {
+    const int t0 = g_vqb_trace_tile;
+    if (on && it >= t0 && it <= t0 + 1) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_vqb_trace_vq[(it - 1) * 16 + i] = t;
+        g_vqb_trace_vq[(it - t0) * 16 + i] = t;
     }
 }
 
@@ -128,6 +136,19 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     unsigned char *sm = smem_raw + (sbase - raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto kmark = [&](int i) {          // kernel-level timeline of CTA 0 (slots 32..), VQB_TC_FLAGS & 8
+        if ((p.flags & 8) && blockIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            g_vqb_trace_vq[32 + i] = t;
+        }
+    };
+    if (tid == 128) kmark(0);
+    if (tid == 128 && (p.flags & 8) && blockIdx.x < 256) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_vqb_cta_t[2 * blockIdx.x] = t;
+    }
     const uint32_t bars = sbase + OFF_BAR;
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     float *bsm = reinterpret_cast<float *>(sm + OFF_B);
@@ -308,6 +329,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             return sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128;
         };
 
+        if (tid == 128) kmark(1);          // setup + codebook norms done
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
@@ -348,7 +370,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 const float *bch = bsm + es * CN + h * 128;
                 const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
                 const int gbase = (c * CN + h * 128) / 8;
-                float va[32], vb[32];
+                float va[32], vb[32], warm[8];
                 auto process = [&](const float (&v)[32], int j) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -367,11 +389,28 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                             }
                         }
                         const float gm = ptx::fmin3(ptx::fmin3(s0, s1, s2), ptx::fmin3(s3, s4, s5), fminf(s6, s7));
-                        // branch-free push: always write slot min(cnt, LCAP-1), keep it when in range
-                        lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
-                        cnt += (gm <= thr) ? 1 : 0;
-                        run_min = fminf(run_min, gm);
+                        if (c == 0 && j < 2) {
+                            // warm-up: the first 8 group minima only seed the running minimum; they are
+                            // pushed afterwards against min8 + tau.  A scan that pushes every record low
+                            // lists H(64) ~ 4.7 groups per thread with a long tail; list overflows (-> exact
+                            // scan of all K codes by the whole warp) cost about half of the kernel time.
+                            warm[j * 4 + g] = gm;
+                            run_min = fminf(run_min, gm);
+                        } else {
+                            // branch-free push: always write slot min(cnt, LCAP-1), keep it when in range
+                            lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
+                            cnt += (gm <= thr) ? 1 : 0;
+                            run_min = fminf(run_min, gm);
+                            thr = run_min + tau;
+                        }
+                    }
+                    if (c == 0 && j == 1) {
                         thr = run_min + tau;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(warm[i], __int_as_float(gbase + i));
+                            cnt += (warm[i] <= thr) ? 1 : 0;
+                        }
                     }
                 };
                 if (!(p.flags & 2)) {
@@ -565,6 +604,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             vq_mark(tr, it, 11);
         }
 
+        if (tid == 128) { kmark(2); g_vqb_trace_vq[40] = (unsigned long long)it; }   // all tiles done
         // ---- CTA reduction of the SSE partial, histogram flush ----
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
@@ -583,8 +623,17 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             }
     }
 
+    if (tid == 128) kmark(3);              // epilogue finished (histogram flushed)
     ptx::tc_fence_before();
     __syncthreads();
+    if (tid == 128) kmark(4);              // every warp done (producer drained its TMA stores)
+    if (tid == 128 && (p.flags & 8) && blockIdx.x < 256) {
+        unsigned long long t;
+        unsigned sm_id;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_id));
+        g_vqb_cta_t[2 * blockIdx.x + 1] = (t << 10) | (sm_id & 1023);      // end time with the SM id in the low bits
+    }
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -660,6 +709,7 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     const long long ntiles = (N + TM - 1) / TM;
     int grid = (int)(ntiles < sms ? ntiles : sms);
     if (grid > 256) grid = 256;
+    if (const char *ge = getenv("VQB_TC_GRID")) { const int g = atoi(ge); if (g > 0 && g < grid) grid = g; }   // experiments
     VqTcParams p;
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
@@ -667,6 +717,11 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     {
         const char *fl = getenv("VQB_TC_FLAGS");
         p.flags = fl ? atoi(fl) : 0;
+        const char *tt = getenv("VQB_TC_TRACE_TILE");
+        if (tt && (p.flags & 8)) {
+            const int v = atoi(tt);
+            cudaMemcpyToSymbolAsync(g_vqb_trace_tile, &v, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+        }
     }
     if (dbg) vq_tc_kernel<true><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     else if (cudaError_t le = vqb_launch(vq_tc_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)) return (int)le;
