@@ -6,6 +6,7 @@ top-level ``models`` package so ``from models.vqvae import VQVAE`` drops in).
 """
 from .modules import (Decoder, Encoder, ResidualLayer, ResidualStack, VectorQuantizer, VQVAE,  # noqa: F401
                       get_precision, precision, set_precision)
+from .pipeline import HostPipeline, HostResult  # noqa: F401
 
 __all__ = ["VQVAE", "VectorQuantizer", "Encoder", "Decoder", "ResidualLayer", "ResidualStack",
-           "set_precision", "get_precision", "precision"]
+           "set_precision", "get_precision", "precision", "HostPipeline", "HostResult"]

@@ -14,9 +14,11 @@ namespace {
 
 constexpr int CI_THREADS = 256;
 
+template <int COUT>
 __global__ void __launch_bounds__(CI_THREADS)
 conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, const float *__restrict__ bias,
-                  float *__restrict__ y, int B, int H, int W, int Cout, int relu) {
+                  float *__restrict__ y, int B, int H, int W, int relu) {
+    constexpr int Cout = COUT;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -44,11 +46,24 @@ conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, con
     for (int c = tid; c < Cout; c += CI_THREADS) bias_s[c] = bias ? __ldg(bias + c) : 0.f;
 
     // ---- B operand: wp[k][co] (k = (r*4+s)*3 + c, 48 rows) -> K-major swizzled rows of 64 (zero padded) ----
-    for (int i = tid; i < Cout * 64; i += CI_THREADS) {
-        const int co = i % Cout, k = i / Cout;                 // co fastest: coalesced reads of wp
-        const float v = k < 48 ? __ldg(wp + (size_t)k * Cout + co) : 0.f;
-        const int atom = k >> 5, kk = k & 31;
-        *reinterpret_cast<float *>(sm + b_off + atom * b_atom + co * 128 + (((kk >> 2) ^ (co & 7)) << 4) + (kk & 3) * 4) = v;
+    {
+        // all weight loads of the thread in flight before the first store (a rolled loop serialises
+        // Cout*64/256 L2 round trips: it was half of this kernel's 21 us)
+        constexpr int NB = COUT * 64 / CI_THREADS;
+        float wv[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int i = tid + u * CI_THREADS;
+            const int co = i % COUT, k = i / COUT;             // co fastest: coalesced reads of wp
+            wv[u] = k < 48 ? __ldg(wp + (size_t)k * COUT + co) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int i = tid + u * CI_THREADS;
+            const int co = i % COUT, k = i / COUT;
+            const int atom = k >> 5, kk = k & 31;
+            *reinterpret_cast<float *>(sm + b_off + atom * b_atom + co * 128 + (((kk >> 2) ^ (co & 7)) << 4) + (kk & 3) * 4) = wv[u];
+        }
     }
     pdl_launch_dependents();
     pdl_wait();                    // x may be written by the previous kernel / copy
@@ -127,7 +142,7 @@ conv_in_tc_kernel(const float *__restrict__ x, const float *__restrict__ wp, con
 }  // namespace
 
 bool conv_in_tc_supported(int Cin, int Cout, int H, int W, const void *y) {
-    return Cin == 3 && Cout % 64 == 0 && Cout >= 64 && Cout <= 256 && H % 2 == 0 && W % 2 == 0 &&
+    return Cin == 3 && (Cout == 64 || Cout == 128) && H % 2 == 0 && W % 2 == 0 &&
            (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
 
@@ -138,13 +153,20 @@ int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float 
     const long long blocks = (npix + 127) / 128;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
     const int smem = 2 * 16384 + 2 * Cout * 128 + 16 + Cout * 4 + 1024;
-    static int attr_max = 0;
-    if (smem > attr_max) {
-        cudaError_t e = cudaFuncSetAttribute(conv_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_in_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             2 * 16384 + 2 * 64 * 128 + 16 + 64 * 4 + 1024);
         if (e != cudaSuccess) return (int)e;
-        attr_max = smem;
+        e = cudaFuncSetAttribute(conv_in_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 2 * 16384 + 2 * 128 * 128 + 16 + 128 * 4 + 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
     }
-    if (cudaError_t le = vqb_launch(conv_in_tc_kernel, dim3((unsigned)blocks), dim3(CI_THREADS), (size_t)smem, s, x, wp, bias, y, B, H, W, Cout, relu)) return (int)le;
+    cudaError_t le;
+    if (Cout == 64) le = vqb_launch(conv_in_tc_kernel<64>, dim3((unsigned)blocks), dim3(CI_THREADS), (size_t)smem, s, x, wp, bias, y, B, H, W, relu);
+    else le = vqb_launch(conv_in_tc_kernel<128>, dim3((unsigned)blocks), dim3(CI_THREADS), (size_t)smem, s, x, wp, bias, y, B, H, W, relu);
+    if (le != cudaSuccess) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
