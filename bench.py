@@ -464,10 +464,14 @@ def kernel_roofline(top, B, S, K, D, peaks, precision):
         return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
     parts = label.split()
-    if parts[0] == "res":                       # "res C->Cmid->C HxW": 3x3 C->Cmid then 1x1 Cmid->C
+    if parts[0] == "res":                       # "res [xN] C->Cmid->C HxW": N x (3x3 C->Cmid then 1x1 Cmid->C)
+        napp = 1
+        if parts[1].startswith("x"):
+            napp = int(parts[1][1:])
+            parts = [parts[0]] + parts[2:]
         c, cm, _ = (int(v) for v in parts[1].split("->"))
         h, w = (int(v) for v in parts[2].split("x"))
-        flops = 2.0 * B * h * w * (9 * c * cm + cm * c)
+        flops = 2.0 * napp * B * h * w * (9 * c * cm + cm * c)
         tensor_peak = peaks["bf16"] * (1.0 if precision == "bf16" else 0.5)
         ach = flops / (ms * 1e-3) / 1e12
         return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",

@@ -98,6 +98,20 @@ int vqb_residual_layer_f32(const float *r, const float *w1_packed, const float *
                            float *out, float *tmp, int B, int H, int W, int C, int Cmid,
                            int relu_out, int precision, void *stream);
 
+/* ---- a whole ResidualStack, residual.py:45-51 --------------------------------------
+ * n_layers applications of ONE shared-weight layer (residual.py:43 builds the list as
+ * [layer] * n), each followed by the ReLU its consumer applies (the next layer's in-place
+ * ReLU, or the stack's F.relu at :50):  r_{i+1} = relu( r_i + W2 . relu( W1 (*) r_i ) ),
+ * r_0 = r = relu(stack input), out = r_{n_layers}.   r, out NHWC (B,H,W,C).
+ * scratch: B*H*W*C floats (needed when n_layers > 1; used when the applications run as
+ * separate launches), tmp: B*H*W*Cmid floats (FFMA fallback only).
+ * With precision != VQB_FP32, whole images per 128-pixel tile (W <= 8, H <= 16) and the
+ * layer shape vqb_residual_layer_f32 accepts, ALL applications run inside ONE tcgen05
+ * kernel: the activation tile stays in shared memory and is rewritten in place.        */
+int vqb_residual_stack_f32(const float *r, const float *w1_packed, const float *w2_packed,
+                           float *out, float *scratch, float *tmp, int B, int H, int W, int C,
+                           int Cmid, int n_layers, int precision, void *stream);
+
 /* ---- VectorQuantizer.forward, quantizer.py:45-76 --------------------------------
  * z        (N, D) fp32 pixel rows (= z.permute(0,2,3,1).view(-1, e_dim), :45-46)
  * codebook (K, D) fp32 embedding.weight (:26)

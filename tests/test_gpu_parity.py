@@ -327,3 +327,34 @@ def test_fused_residual_layer_tc_vs_oracle(B, H, W, C, Cmid, relu_out):
     for prec, atol in ((FP32, 1e-5), (TF32, 6e-3)):
         y = ops.residual_layer(rn, p1, p2, B=B, H=H, W=W, C=C, Cmid=Cmid, relu_out=relu_out, precision=prec)
         np.testing.assert_allclose(y.cpu().numpy().transpose(0, 3, 1, 2), ref, atol=atol, rtol=2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,C,Cmid,n", [(256, 8, 8, 128, 32, 2), (5, 8, 8, 128, 32, 3), (3, 6, 7, 128, 32, 2),
+                                            (9, 4, 4, 64, 32, 4), (2, 16, 16, 128, 32, 2), (1, 8, 8, 128, 32, 1)])
+def test_fused_residual_stack_tc(B, H, W, C, Cmid, n):
+    """vqb_residual_stack_f32 (residual.py:45-51): all n shared-weight applications in ONE tcgen05 launch when a
+    128-pixel tile holds whole images.  Same arithmetic as n separate vqb_residual_layer_f32 launches, so the two
+    are bit-identical; both are held to the oracle at the TF32 tolerance, the fp32 mode at 1e-5 per layer."""
+    from vqvae_b200 import ops
+    from vqvae_b200._lib import FP32, TF32
+    rng = np.random.RandomState(B * 1000 + H * 100 + C + n)
+    r = np.maximum(rng.standard_normal((B, C, H, W)).astype(np.float32), 0)
+    w1 = (rng.standard_normal((Cmid, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32)
+    w2 = (rng.standard_normal((C, Cmid, 1, 1)) / np.sqrt(Cmid)).astype(np.float32)
+    ref = r
+    for _ in range(n):
+        ref = np.maximum(ref + cref.conv2d(np.maximum(cref.conv2d(ref, w1, None, 1, 1), 0), w2, None, 1, 0), 0)
+    rn = _cuda(np.ascontiguousarray(r.transpose(0, 2, 3, 1)))
+    p1, p2 = ops.pack_conv_weight(_cuda(w1), False), ops.pack_conv_weight(_cuda(w2), False)
+    for prec, atol in ((FP32, 1e-5 * n), (TF32, 6e-3 * n)):
+        l0 = ops.launch_count()
+        y = ops.residual_stack(rn, p1, p2, B=B, H=H, W=W, C=C, Cmid=Cmid, n_layers=n, precision=prec)
+        launches = ops.launch_count() - l0
+        np.testing.assert_allclose(y.cpu().numpy().transpose(0, 3, 1, 2), ref, atol=atol, rtol=2e-3 * n)
+        seq = rn
+        for _ in range(n):
+            seq = ops.residual_layer(seq, p1, p2, B=B, H=H, W=W, C=C, Cmid=Cmid, relu_out=True, precision=prec)
+        assert torch.equal(y, seq)
+        if prec == TF32 and W <= 8 and H <= 16:
+            assert launches == 1, launches          # the fused path really ran
+    assert torch.equal(rn.cpu(), torch.from_numpy(np.ascontiguousarray(r.transpose(0, 2, 3, 1))))   # input untouched

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vqb_debug_read_trace_vq": (_i, [_vp, _i]),
     "vqb_debug_read_cta_times": (_i, [_vp, _i]),
     "vqb_residual_layer_f32": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
+    "vqb_residual_stack_f32": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "vqb_debug_vq_scores_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
 }
 

@@ -18,7 +18,7 @@ int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, fl
                           int Cout, int relu, cudaStream_t s);
 bool res_tc_supported(int C, int Cmid, const void *r, const void *out);
 int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
-                  int Cmid, int relu_out, cudaStream_t s);
+                  int Cmid, int relu_out, int napp, cudaStream_t s);
 bool conv_in_tc_supported(int Cin, int Cout, int H, int W, const void *y);
 int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float *y, int B, int H, int W, int Cout,
                       int relu, cudaStream_t s);
@@ -224,11 +224,36 @@ extern "C" int vqb_residual_layer_f32(const float *r, const float *w1_packed, co
     if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
     if (precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out))
         return launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C, Cmid,
-                             relu_out, (cudaStream_t)stream);
+                             relu_out, 1, (cudaStream_t)stream);
     // two launches through the generic path (residual.py:20-24 then :23-24,:28)
     int rc = vqb_conv2d_f32(r, w1_packed, nullptr, nullptr, tmp, B, C, H, W, Cmid, 3, 3, 1, 1, 0, VQB_NHWC, VQB_NHWC, 1,
                             precision, stream);
     if (rc) return rc;
     return vqb_conv2d_f32(tmp, w2_packed, nullptr, r, out, B, Cmid, H, W, C, 1, 1, 1, 0, 0, VQB_NHWC, VQB_NHWC,
                           relu_out, precision, stream);
+}
+
+extern "C" int vqb_residual_stack_f32(const float *r, const float *w1_packed, const float *w2_packed, float *out,
+                                      float *scratch, float *tmp, int B, int H, int W, int C, int Cmid, int n_layers,
+                                      int precision, void *stream) {
+    if (!r || !w1_packed || !w2_packed || !out || !tmp) return VQB_ERR_BAD_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cmid <= 0 || n_layers < 1) return VQB_ERR_BAD_ARG;
+    if (n_layers > 1 && !scratch) return VQB_ERR_BAD_ARG;
+    if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
+    static const bool fuse = [] { const char *e = getenv("VQB_RES_FUSE"); return !(e && e[0] == '0'); }();
+    if (fuse && n_layers > 1 && precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out)) {
+        // all applications in ONE launch: the activation never leaves shared memory between them
+        const int rc = launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C,
+                                     Cmid, 1, n_layers, (cudaStream_t)stream);
+        if (rc != VQB_ERR_UNSUPPORTED) return rc;
+    }
+    // one launch per application, ping-ponging so that the last one lands in `out`
+    const float *src = r;
+    for (int i = 0; i < n_layers; ++i) {
+        float *dst = ((n_layers - 1 - i) % 2 == 0) ? out : scratch;
+        const int rc = vqb_residual_layer_f32(src, w1_packed, w2_packed, dst, tmp, B, H, W, C, Cmid, 1, precision, stream);
+        if (rc) return rc;
+        src = dst;
+    }
+    return 0;
 }

@@ -48,6 +48,9 @@ struct ResTcParams {
     int BH, BN, tiles_x, tiles_y;          // tile = 8 px wide x (BH rows x BN images = 16)
     int stages;
     int relu_out;
+    int napp;               // applications of the (shared-weight) layer chained inside the kernel (residual.py:45-50);
+                            // > 1 only in staged mode with tiles that hold whole images: the activation then stays
+                            // in the halo buffers (borders = the conv's zero padding) and is rewritten in place
     int staged;             // 1: all halo chunks resident (skip read from smem) and the output tile is
                             //    staged in smem (ring + A2 + W2 region) and TMA-stored
     int flags;              // perf experiments (env VQB_RES_FLAGS): 1 = skip GEMM1 MMAs, 2 = skip W1 loads/waits
@@ -81,7 +84,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const uint32_t d2full = bars + 8u * (2 * RT_MAX_STAGES + 3);
     auto hfull = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + b); };
     auto hempty = [&](int b) { return bars + 8u * (2 * RT_MAX_STAGES + 4 + RT_MAX_CHUNKS + b); };
-    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS);
+    const uint32_t actready = bars + 8u * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS);   // in-place activation rewritten
+    constexpr int RT_MISC = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS + 2);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + RT_MISC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -104,6 +108,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_init(d1full, 1);
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
+        ptx::mbar_init(actready, 4);                        // one arrival per epilogue warp
         for (int b = 0; b < hbufs; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
         ptx::prefetch_tmap(&tma_out);
         ptx::fence_mbar_init();
@@ -138,11 +143,12 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 for (int a = 0; a < matoms; ++a)
                     ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
             }
-            const int prefill = S < 9 * chunks ? S : 9 * chunks;
+            const int ksteps = 9 * chunks * p.napp;     // the same W1 tiles stream once per application
+            const int prefill = S < ksteps ? S : ksteps;
             if (leader)
                 for (int i = 0; i < prefill; ++i) {
                     ptx::mbar_expect_tx(bars + 8u * i, (uint32_t)stage_bytes);
-                    ptx::tma_load_2d(sbase + ring_off + i * stage_bytes, &tma_w1, bars + 8u * i, (i / 9) * 32, (i % 9) * p.Cmid);
+                    ptx::tma_load_2d(sbase + ring_off + i * stage_bytes, &tma_w1, bars + 8u * i, ((i / 9) % chunks) * 32, (i % 9) * p.Cmid);
                 }
             pdl_wait();                                 // the input activation is the previous layer's output
             for (int c = 0; c < hbufs; ++c) load_halo(c);
@@ -150,6 +156,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES;
             uint32_t dst = sbase + ring_off;
             int kidx = 0;
+            for (int app = 0; app < p.napp; ++app)
             for (int c = 0; c < chunks; ++c) {
                 if (c >= 1 && c + 1 < chunks && c + 1 >= hbufs) load_halo(c + 1);
 #pragma unroll
@@ -179,56 +186,75 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             const uint32_t a_hi = ptx::desc_hi_sw128(RT_WP * 128), b_hi = ptx::desc_hi_sw128(1024);
             const uint32_t rs16 = (uint32_t)(p.BN * RT_WP * 128) >> 4;      // one padded halo row, in 16-byte units
             const uint32_t b_lo0 = (sbase + ring_off) >> 4, b_step = (uint32_t)stage_bytes >> 4;
-            uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES, b_lo = b_lo0, acc = 0;
-            for (int c = 0; c < chunks; ++c) {
-                const int hb = c % hbufs;
-                ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
-                if (leader) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
-                const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    ptx::mbar_wait(full_bar, par);
+            uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES, b_lo = b_lo0;
+            for (int app = 0; app < p.napp; ++app) {
+                const uint32_t ap = (uint32_t)(app & 1);
+                uint32_t acc = 0;
+                if (app > 0) {
+                    // the epilogue has rewritten the activation in place (and drained D1/D2 of the previous application)
+                    ptx::mbar_wait(actready, ap ^ 1u);
                     ptx::tc_fence_after();
-                    // tap (dy,dx) = (t/3-1, t%3-1): the halo tile read (dy+1) padded rows and (dx+1) pixels
-                    // further in; base_offset stays 0 (the swizzle phase comes from the absolute address)
-                    const uint32_t a_lo = h_lo + (uint32_t)(t / 3) * rs16 + (uint32_t)(t % 3) * 8u;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc1, acc);
-                        acc = 1;
-                    }
-                    ++st; full_bar += 8; b_lo += b_step;
-                    if ((st & (RT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
-                    if (st == (uint32_t)S) {
-                        st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * RT_MAX_STAGES; b_lo = b_lo0;
-                    }
                 }
-                if (leader) ptx::tc_commit(hempty(hb));     // chunk done: its halo buffer may be refilled
+                for (int c = 0; c < chunks; ++c) {
+                    const int hb = c % hbufs;
+                    ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
+                    if (leader && app == 0) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
+                    const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        ptx::mbar_wait(full_bar, par);
+                        ptx::tc_fence_after();
+                        // tap (dy,dx) = (t/3-1, t%3-1): the halo tile read (dy+1) padded rows and (dx+1) pixels
+                        // further in; base_offset stays 0 (the swizzle phase comes from the absolute address)
+                        const uint32_t a_lo = h_lo + (uint32_t)(t / 3) * rs16 + (uint32_t)(t % 3) * 8u;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc1, acc);
+                            acc = 1;
+                        }
+                        ++st; full_bar += 8; b_lo += b_step;
+                        if ((st & (RT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
+                        if (st == (uint32_t)S) {
+                            st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * RT_MAX_STAGES; b_lo = b_lo0;
+                        }
+                    }
+                    if (leader && !p.staged) ptx::tc_commit(hempty(hb));     // chunk done: its halo buffer may be refilled
+                    __syncwarp();
+                }
+                if (leader) { ptx::tc_commit(d1full); if (app == 0) trace_mark(8); }    // all GEMM1 MMAs issued
+                // GEMM2 once the epilogue has written relu(D1) as the A2 operand
+                if (app == 0) ptx::mbar_wait(w2full, 0);
+                ptx::mbar_wait(a2ready, ap);
+                ptx::tc_fence_after();
+                for (int a = 0; a < matoms; ++a)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        if (leader)
+                            ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
+                                          ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
+                                          (a > 0 || kk > 0) ? 1u : 0u);
+                if (leader) { ptx::tc_commit(d2full); if (app == 0) trace_mark(11); }   // GEMM2 issued
                 __syncwarp();
             }
-            if (leader) { ptx::tc_commit(d1full); trace_mark(8); }    // all GEMM1 MMAs issued
-            // GEMM2 once the epilogue has written relu(D1) as the A2 operand
-            ptx::mbar_wait(w2full, 0);
-            ptx::mbar_wait(a2ready, 0);
-            ptx::tc_fence_after();
-            for (int a = 0; a < matoms; ++a)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    if (leader)
-                        ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
-                                      ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
-                                      (a > 0 || kk > 0) ? 1u : 0u);
-            if (leader) { ptx::tc_commit(d2full); trace_mark(11); }   // GEMM2 issued
         }
     } else if (warp < 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         pdl_wait();     // (non-staged path reads the skip tensor from global memory)
+        const int bw = row & 7, grp = row >> 3;             // row = (y * BN + bn) * 8 + x
+        const int bn = grp % p.BN, bh = grp / p.BN;
+        const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
+        const bool valid = gx < p.W && gy < p.H && n < p.B;
+        const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.C;
+        const int hrow = ((bh + 1) * p.BN + bn) * RT_WP + bw + 1;      // this pixel's row of a halo buffer
+        for (int app = 0; app < p.napp; ++app) {
+        const uint32_t ap = (uint32_t)(app & 1);
+        const bool last = app + 1 == p.napp;
         // ---- epilogue 1: relu(D1) -> A2 operand in shared memory ----
-        ptx::mbar_wait_sleep(d1full, 0);
+        ptx::mbar_wait_sleep(d1full, ap);
         ptx::tc_fence_after();
-        if (tid == 0) trace_mark(9);                 // GEMM1 complete (epilogue sees D1)
+        if (tid == 0 && app == 0) trace_mark(9);                 // GEMM1 complete (epilogue sees D1)
         for (int a = 0; a < matoms; ++a) {
             float v[32];
             ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
@@ -245,22 +271,42 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a2ready);
-        if (tid == 0) trace_mark(10);                // A2 written
+        if (tid == 0 && app == 0) trace_mark(10);                // A2 written
 
-        // ---- epilogue 2: D2 + skip -> ReLU -> NHWC store ----
-        const int bw = row & 7, grp = row >> 3;             // row = (y * BN + bn) * 8 + x
-        const int bn = grp % p.BN, bh = grp / p.BN;
-        const int gx = gx0 + bw, gy = gy0 + bh, n = n0 + bn;
-        const bool valid = gx < p.W && gy < p.H && n < p.B;
-        const long long ob = (((long long)n * p.H + gy) * p.W + gx) * p.C;
-        ptx::mbar_wait_sleep(d2full, 0, 64);
+        // ---- epilogue 2: D2 + skip -> ReLU -> next application's input / NHWC store ----
+        ptx::mbar_wait_sleep(d2full, ap, 64);
         ptx::tc_fence_after();
-        if (tid == 0) trace_mark(12);                // GEMM2 complete
+        if (tid == 0 && app == 0) trace_mark(12);                // GEMM2 complete
+        if (!last) {
+            // chained application (staged mode, whole images per tile): r_{a+1} = act(r_a + D2) replaces r_a in
+            // the halo buffers, same thread, same address; pixels outside the image stay zero (= conv padding)
+            for (int c0 = 0; c0 < p.C; c0 += 32) {
+                float v[32];
+                ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
+                ptx::tmem_ld_wait32(v);
+                unsigned char *srow = sm + (c0 >> 5) * halo_bytes + hrow * 128;
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    float4 *ptr = reinterpret_cast<float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
+                    const float4 sk = *ptr;
+                    float4 o = make_float4(v[c16 * 4] + sk.x, v[c16 * 4 + 1] + sk.y, v[c16 * 4 + 2] + sk.z, v[c16 * 4 + 3] + sk.w);
+                    if (p.relu_out) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *ptr = o;
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(actready);
+            continue;
+        }
         if (p.staged) {
             // skip = centre tap of the resident halo tiles; output tile staged in shared memory (over the
             // W1 ring + A2 + W2, all dead once GEMM2 has completed) in MMA row order and TMA-stored:
             // no global skip loads, no scattered 16-byte stores.
-            const int hrow = ((bh + 1) * p.BN + bn) * RT_WP + bw + 1;
             for (int c0 = 0; c0 < p.C; c0 += 32) {
                 float v[32];
                 ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
@@ -304,6 +350,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 }
             }
         }
+        }   // applications
     }
     if (tid == 0) trace_mark(13);                    // epilogue 2 stores issued
     ptx::tc_fence_before();
@@ -326,14 +373,19 @@ bool res_tc_supported(int C, int Cmid, const void *r, const void *out) {
 }
 
 // w1_tc: [9][Cmid][C], w2_tc: [1][C][Cmid]  (the K-major halves of vqb_pack_conv_weight_f32)
+// napp > 1 chains that many applications of the layer in one launch; it needs tiles that hold whole images
+// (W <= 8, H <= 16) and the staged shared-memory layout, else VQB_ERR_UNSUPPORTED (the caller then launches
+// the applications one by one).
 int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float *out, int B, int H, int W, int C,
-                  int Cmid, int relu_out, cudaStream_t s) {
-    if (!res_tc_supported(C, Cmid, r, out)) return VQB_ERR_UNSUPPORTED;
+                  int Cmid, int relu_out, int napp, cudaStream_t s) {
+    if (!res_tc_supported(C, Cmid, r, out) || napp < 1) return VQB_ERR_UNSUPPORTED;
+    if (napp > 1 && !relu_out) return VQB_ERR_UNSUPPORTED;      // a chained layer input must be relu(x)
     ResTcParams q;
     {
         const char *fl = getenv("VQB_RES_FLAGS");
         q.flags = fl ? atoi(fl) : 0;
     }
+    q.napp = napp;
     q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
     q.BH = rt_pow2_ceil(H) < 16 ? rt_pow2_ceil(H) : 16;
     q.BN = 16 / q.BH;
@@ -367,7 +419,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     const int chunks = C / 32;
     const int halo_b = (q.BH + 2) * q.BN * RT_WP * 128;
     const int tail = (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128;            // A2 + W2
-    const int misc = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS) + 16 + 1024;
+    const int misc = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS + 2) + 16 + 1024;
     // staged mode: every halo chunk resident + a ring that, together with A2 + W2, holds the 128 x C output tile
     int stages = 0;
     q.staged = 0;
@@ -381,6 +433,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
             stages = st;
         }
     }
+    if (napp > 1 && !(q.staged && q.tiles_x == 1 && q.tiles_y == 1)) return VQB_ERR_UNSUPPORTED;
     const int hbufs = q.staged ? chunks : (chunks < RT_HALO_BUFS ? chunks : RT_HALO_BUFS);
     const int fixed = hbufs * halo_b + tail + misc;
     if (!q.staged) {

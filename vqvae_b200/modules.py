@@ -144,9 +144,17 @@ class ResidualStack(nn.Module):
 
     def _apply_nhwc(self, r, B, H, W):
         """r = relu(stack input), NHWC.  Output = the stack's result (post F.relu)."""
-        for layer in self.stack:
-            r = layer._apply_nhwc(r, B, H, W, relu_out=True)
-        return r
+        if len(self.stack) == 0:
+            return r
+        layer = self.stack[0]
+        if any(l is not layer for l in self.stack):      # not the reference's [layer] * n construction
+            for l in self.stack:
+                r = l._apply_nhwc(r, B, H, W, relu_out=True)
+            return r
+        c1, c2 = layer.res_block[1], layer.res_block[3]
+        return ops.residual_stack(r, _PACKED.get(c1.weight, False), _PACKED.get(c2.weight, False), B=B, H=H, W=W,
+                                  C=c1.in_channels, Cmid=c1.out_channels, n_layers=len(self.stack),
+                                  precision=PRECISIONS[get_precision()])
 
     def forward(self, x):
         ch = self.stack[0].res_block[1].in_channels if len(self.stack) else x.shape[1]

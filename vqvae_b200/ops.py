@@ -111,6 +111,23 @@ def residual_layer(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, relu_out, preci
     return out
 
 
+def residual_stack(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, n_layers, precision=FP32):
+    """n_layers applications of one shared-weight layer, each followed by ReLU, on NHWC buffers
+    (vqb_residual_stack_f32; one kernel in tensor-core mode when a tile holds whole images)."""
+    _require_cuda(r, "input")
+    if n_layers < 1:
+        return r
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=r.device)
+    scratch = torch.empty((B, H, W, C), dtype=torch.float32, device=r.device) if n_layers > 1 else out
+    tmp = torch.empty((B, H, W, Cmid), dtype=torch.float32, device=r.device)
+    span = _Span(f"res x{n_layers} {C}->{Cmid}->{C} {H}x{W}")
+    check(lib().vqb_residual_stack_f32(r.data_ptr(), w1_packed.data_ptr(), w2_packed.data_ptr(), out.data_ptr(),
+                                       scratch.data_ptr(), tmp.data_ptr(), B, H, W, C, Cmid, n_layers, precision,
+                                       _stream()), "residual_stack")
+    span.done()
+    return out
+
+
 def vq_forward(z_rows, codebook):
     """Fused VectorQuantizer core on (N,D) rows -> (idx int64 (N,), zq (N,D), sse f64 (1,),
     hist int32 (K,))."""

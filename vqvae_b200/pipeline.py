@@ -14,7 +14,9 @@ batch still goes host -> HBM -> kernels -> host; only the waiting is overlapped.
         if done is not None: consume(done)  # done.loss, done.x_hat (host), done.perplexity
     for done in pipe.drain(): consume(done)
 
-A result's host tensors belong to its slot and are overwritten ``depth`` pushes later.
+A result's host tensors belong to a slot that the NEXT ``push`` reuses: read (or copy) them before
+pushing again.  (``depth`` + 1 slots exist so that the result handed out by a push is not the slot
+that push refills.)
 """
 from __future__ import annotations
 
@@ -84,7 +86,9 @@ class HostPipeline:
             self._copy_in = torch.cuda.Stream()
             self._compute = torch.cuda.Stream()
             self._copy_out = torch.cuda.Stream()
-            self._slots = [_Slot(model, self.shape, self.device, use_graph) for _ in range(depth)]
+            # depth in flight + the one whose result the caller is still reading
+            self._slots = [_Slot(model, self.shape, self.device, use_graph) for _ in range(depth + 1)]
+        self.depth = depth
         self._inflight: Deque[_Slot] = deque()
         self._count = 0
 
@@ -100,7 +104,7 @@ class HostPipeline:
         if tuple(x_host.shape) != self.shape or x_host.dtype != torch.float32 or x_host.device.type != "cpu":
             raise ValueError(f"expected a float32 host tensor of shape {self.shape}")
         done = None
-        if len(self._inflight) == len(self._slots):
+        if len(self._inflight) == self.depth:
             done = self._finish(self._inflight.popleft())
         slot = self._slots[self._count % len(self._slots)]
         assert not slot.busy
