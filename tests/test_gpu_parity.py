@@ -157,7 +157,12 @@ TC_CONV_CASES = [
     (2, 64, 16, 16, 3, 4, 2, 1, True, 1, 0, False, False),     # decoder.py:34-35: 3x3-neighbourhood GEMM + pixel shuffle
     (1, 32, 5, 9, 2, 4, 2, 1, True, 1, 0, True, False),        # same, ragged tile, Cout=2
     (2, 3, 32, 32, 64, 4, 2, 1, False, 0, 1, True, False),     # encoder.py:29-31: hand-built im2col tile
-    (3, 3, 12, 20, 128, 4, 2, 1, False, 0, 1, False, False),   # same, partial last tile, Cout=128
+    (3, 3, 12, 20, 128, 4, 2, 1, False, 0, 1, False, False),   # same, partial last tile, Cout=128 (generic gather)
+    (3, 3, 64, 64, 64, 4, 2, 1, False, 0, 1, True, False),     # staged-rows fast path, 4 output rows per tile
+    (1, 3, 8, 256, 64, 4, 2, 1, False, 0, 1, False, False),    # fast path, one output row per tile (OW = 128)
+    (5, 3, 16, 16, 64, 4, 2, 1, False, 0, 1, True, False),     # tile straddles images: generic gather + TMA store
+    (2, 3, 32, 32, 128, 4, 2, 1, False, 0, 1, True, False),    # fast path, Cout=128 (direct stores)
+    (3, 3, 6, 8, 64, 4, 2, 1, False, 0, 1, True, False),       # partial tile (36 pixels), TMA store clips
 ]
 
 

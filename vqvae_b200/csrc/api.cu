@@ -30,6 +30,11 @@ int launch_conv_halo(const ConvLaunch &p, const float *w_tc, cudaStream_t s);
 bool conv_tc_supported(const ConvLaunch &p);
 int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
 
+int vqb_halo_wp() {
+    static const int wp = [] { const char *e = getenv("VQB_HALO_WP"); return (e && atoi(e) == 16) ? 16 : 10; }();
+    return wp;
+}
+
 int vqb_pdl_enabled() {
     static int on = -1;
     if (on < 0) {

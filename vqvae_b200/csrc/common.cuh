@@ -38,6 +38,7 @@ extern unsigned long long g_vqb_launches;
 // TMEM allocation, tensor-map prefetch) while this one drains; it blocks in pdl_wait() until the previous
 // grid has completed and its writes are visible.  VQB_PDL=0 in the environment disables the attribute.
 int vqb_pdl_enabled();
+int vqb_halo_wp();           // halo tile width of conv_halo.cu / res_tc.cu: 10, or 16 with VQB_HALO_WP=16
 #ifdef __CUDACC__
 #include <utility>
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -24,7 +24,9 @@ constexpr int CH_MAX_STAGES = 32;     // weight-tile ring: as deep as shared mem
 constexpr int CH_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int CH_HALO_BUFS = 2;       // halo tiles are double buffered: chunk c+2 loads while c+1 computes
 constexpr int CH_MAX_CHUNKS = 8;       // Cin <= 256
-constexpr int WP = 16;                 // padded tile width: 8 pixels + halo, multiple of 8
+constexpr int WP_DEFAULT = 10;               // halo tile width: 8 pixels + 1 each side.  Not a multiple of 8 on purpose: the swizzle
+                                     // phase of a row comes from its absolute address, for TMA and UMMA alike, so an
+                                     // 8-row operand group may start at any row (SBO = WP rows); 16 wasted 37 % of the tile
 
 struct ConvHaloParams {
     const float *bias, *skip;
@@ -32,22 +34,11 @@ struct ConvHaloParams {
     int B, H, W, Cin, Cout;
     int BH, BN, tiles_x, tiles_y;
     int stages, relu, bo_mode;
+    int WP;                 // halo tile width in pixels (10, or 16 with VQB_HALO_WP=16)
     int shuffle_cout;       // > 0: the GEMM's 16 columns are (py, px, co) of a k4s2p1 transposed conv with this
                             // many real output channels; the epilogue pixel-shuffles them into the NCHW output
     int tap_w[9], tap_dy[9], tap_dx[9];
 };
-
-__device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int bo_mode) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((WP * 128u) >> 4) << 32;          // SBO: 8-pixel groups are one padded row apart
-    d |= (uint64_t)1 << 46;
-    // base_offset (bits 49-51) stays 0: measured on B200, the tensor core derives the swizzle
-    // phase from the absolute shared-memory address; setting (saddr >> 7) & 7 breaks the result.
-    (void)bo_mode;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
@@ -58,11 +49,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     unsigned char *sm = smem_raw + (sbase - raw);
 
     const int chunks = p.Cin / 32;
+    const int WP = p.WP;
     const int halo_bytes = (p.BH + 2) * p.BN * WP * 128;        // per 32-channel chunk
+    const int halo_stride = (halo_bytes + 1023) & ~1023;        // buffers start on swizzle-pattern boundaries
     const int b_bytes = p.Cout * 128;
     const int S = p.stages;
     const int hbufs = chunks < CH_HALO_BUFS ? chunks : CH_HALO_BUFS;
-    const uint32_t ring_off = (uint32_t)(hbufs * halo_bytes);
+    const uint32_t ring_off = (uint32_t)(hbufs * halo_stride);
     const uint32_t bar_off = ring_off + (uint32_t)(S * b_bytes);
     const uint32_t bars = sbase + bar_off;
     auto bfull = [&](int s) { return bars + 8u * s; };
@@ -112,7 +105,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
             if (c >= CH_HALO_BUFS) ptx::mbar_wait(hempty(b), (uint32_t)(((c / CH_HALO_BUFS) - 1) & 1));
             if (leader) {
                 ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
-                ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+                ptx::tma_load_4d(sbase + b * halo_stride, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
             }
         };
         // weights do not depend on the previous layer: the first ring-full of weight tiles is requested
@@ -154,7 +147,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
         for (int c = 0; c < chunks; ++c) {
             const int hb = c % CH_HALO_BUFS;
             ptx::mbar_wait(hfull(hb), (uint32_t)((c / CH_HALO_BUFS) & 1));
-            const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
+            const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_stride)) >> 4;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 ptx::mbar_wait(full_bar, par);
@@ -280,6 +273,8 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     // dims ordered (c, w, n, h): the BN images of a tile interleave row by row in shared memory
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.B, (uint64_t)p.H};
     const uint64_t strides[3] = {(uint64_t)p.Cin * 4, (uint64_t)p.H * p.W * p.Cin * 4, (uint64_t)p.W * p.Cin * 4};
+    const int WP = vqb_halo_wp();
+    q.WP = WP;
     const uint32_t box[4] = {32u, (uint32_t)WP, (uint32_t)q.BN, (uint32_t)(q.BH + 2)};
     const uint32_t es[4] = {1u, 1u, 1u, 1u};
     int rc = vqb_encode_tmap_4d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.in, dims, strides, box, es,
@@ -289,7 +284,7 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
                             (uint64_t)p.Cin * 4, 32, (uint32_t)p.Cout, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const int chunks = p.Cin / 32;
-    const int halo_bytes = (q.BH + 2) * q.BN * WP * 128;
+    const int halo_bytes = (((q.BH + 2) * q.BN * WP * 128) + 1023) & ~1023;
     const int b_bytes = p.Cout * 128;
     const int hbufs = chunks < CH_HALO_BUFS ? chunks : CH_HALO_BUFS;
     const int fixed = hbufs * halo_bytes + 8 * (2 * CH_MAX_STAGES + 2 * CH_HALO_BUFS + 1) + 8 + 256 * 4 + 1024;

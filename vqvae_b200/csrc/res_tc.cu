@@ -39,7 +39,6 @@ constexpr int RT_GROUP = 4;           // ring stages released per tcgen05.commit
 constexpr int RT_HALO_BUFS = 2;       // double-buffered halo tiles
 constexpr int RT_A_BYTES = 128 * 128;
 constexpr int RT_MAX_CHUNKS = 8;
-constexpr int RT_WP = 16;              // padded tile width (8 pixels + halo), multiple of 8
 
 struct ResTcParams {
     const float *skip;      // r, NHWC (B,H,W,C)
@@ -47,6 +46,7 @@ struct ResTcParams {
     int B, H, W, C, Cmid;
     int BH, BN, tiles_x, tiles_y;          // tile = 8 px wide x (BH rows x BN images = 16)
     int stages;
+    int WP;                 // halo tile width in pixels: 8 + 1 each side = 10 (see conv_halo.cu), or 16 (VQB_HALO_WP)
     int relu_out;
     int napp;               // applications of the (shared-weight) layer chained inside the kernel (residual.py:45-50);
                             // > 1 only in staged mode with tiles that hold whole images: the activation then stays
@@ -67,11 +67,13 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
 
     const int S = p.stages;
     const int chunks = p.C / 32;
+    const int RT_WP = p.WP;
     const int halo_bytes = (p.BH + 2) * p.BN * RT_WP * 128; // per 32-channel chunk
+    const int halo_stride = (halo_bytes + 1023) & ~1023;    // buffers start on swizzle-pattern boundaries
     const int stage_bytes = p.Cmid * 128;                   // W1 tile of one (tap, chunk)
     const int matoms = p.Cmid / 32;                         // 128-byte atoms of the GEMM2 K dimension
     const int hbufs = (p.staged || chunks < RT_HALO_BUFS) ? chunks : RT_HALO_BUFS;
-    const uint32_t ring_off = (uint32_t)(hbufs * halo_bytes);
+    const uint32_t ring_off = (uint32_t)(hbufs * halo_stride);
     const uint32_t a2_off = ring_off + (uint32_t)(S * stage_bytes);    // A2: matoms x [128 rows][128 B]
     const uint32_t w2_off = a2_off + (uint32_t)(matoms * RT_A_BYTES);   // W2: matoms x [C rows][128 B]
     const uint32_t bar_off = w2_off + (uint32_t)(matoms * p.C * 128);
@@ -133,7 +135,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 if (c >= hbufs) ptx::mbar_wait(hempty(b), (uint32_t)(((c / hbufs) - 1) & 1));
                 if (leader) {
                     ptx::mbar_expect_tx(hfull(b), (uint32_t)halo_bytes);
-                    ptx::tma_load_4d(sbase + b * halo_bytes, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
+                    ptx::tma_load_4d(sbase + b * halo_stride, &tma_in, hfull(b), c * 32, gx0 - 1, n0, gy0 - 1);
                 }
             };
             // weights do not depend on the previous layer: W2 and the first ring-full of W1 tiles are
@@ -199,7 +201,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     const int hb = c % hbufs;
                     ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
                     if (leader && app == 0) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
-                    const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_bytes)) >> 4;
+                    const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_stride)) >> 4;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         ptx::mbar_wait(full_bar, par);
@@ -284,7 +286,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 float v[32];
                 ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
                 ptx::tmem_ld_wait32(v);
-                unsigned char *srow = sm + (c0 >> 5) * halo_bytes + hrow * 128;
+                unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
 #pragma unroll
                 for (int c16 = 0; c16 < 8; ++c16) {
                     float4 *ptr = reinterpret_cast<float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
@@ -311,7 +313,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 float v[32];
                 ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
                 ptx::tmem_ld_wait32(v);
-                const unsigned char *srow = sm + (c0 >> 5) * halo_bytes + hrow * 128;
+                const unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
                 unsigned char *orow = sm + ring_off + (c0 >> 5) * RT_A_BYTES + row * 128;
 #pragma unroll
                 for (int c16 = 0; c16 < 8; ++c16) {
@@ -393,6 +395,8 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     q.tiles_y = (H + q.BH - 1) / q.BH;
     const int tiles_n = (B + q.BN - 1) / q.BN;
 
+    const int RT_WP = vqb_halo_wp();
+    q.WP = RT_WP;
     CUtensorMap tin, tw1, tw2, tout;
     // dims ordered (c, w, n, h): the BN images of a tile interleave row by row in shared memory
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)B, (uint64_t)H};
@@ -417,7 +421,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
 
     const int stage_bytes = Cmid * 128;
     const int chunks = C / 32;
-    const int halo_b = (q.BH + 2) * q.BN * RT_WP * 128;
+    const int halo_b = (((q.BH + 2) * q.BN * RT_WP * 128) + 1023) & ~1023;
     const int tail = (Cmid / 32) * RT_A_BYTES + (Cmid / 32) * C * 128;            // A2 + W2
     const int misc = 8 * (2 * RT_MAX_STAGES + 4 + 2 * RT_MAX_CHUNKS + 2) + 16 + 1024;
     // staged mode: every halo chunk resident + a ring that, together with A2 + W2, holds the 128 x C output tile
@@ -428,9 +432,15 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
         int st = (need + stage_bytes - 1) / stage_bytes;
         if (st < RT_GROUP) st = RT_GROUP;
         st = (st + RT_GROUP - 1) / RT_GROUP * RT_GROUP;
-        if (st <= RT_MAX_STAGES && chunks * halo_b + st * stage_bytes + tail + misc <= 227 * 1024 && chunks <= RT_MAX_CHUNKS) {
+        // ... and as deep as shared memory allows beyond that: the W1 tiles in flight (stages x Cmid x 128 B)
+        // over the L2 latency are what feeds GEMM1 (8 stages = 32 KB kept the tensor pipe 14 % busy)
+        int fit = (227 * 1024 - (chunks * halo_b + tail + misc)) / stage_bytes;
+        if (fit > RT_MAX_STAGES) fit = RT_MAX_STAGES;
+        fit -= fit % RT_GROUP;
+        if (st <= fit && chunks <= RT_MAX_CHUNKS) {
             q.staged = 1;
-            stages = st;
+            const int all = (9 * chunks * napp + RT_GROUP - 1) / RT_GROUP * RT_GROUP;
+            stages = fit < all ? fit : (all > st ? all : st);
         }
     }
     if (napp > 1 && !(q.staged && q.tiles_x == 1 && q.tiles_y == 1)) return VQB_ERR_UNSUPPORTED;
