@@ -34,6 +34,8 @@ struct ConvHaloParams {
     int B, H, W, Cin, Cout;
     int BH, BN, tiles_x, tiles_y;
     int stages, relu, bo_mode;
+    int nmma;               // MMA issuer warps (1 or 2): k-step i goes to issuer i % nmma, private accumulators summed
+                            // by the epilogue in a fixed order (see res_tc.cu)
     int WP;                 // halo tile width in pixels (10, or 16 with VQB_HALO_WP=16)
     int shuffle_cout;       // > 0: the GEMM's 16 columns are (py, px, co) of a k4s2p1 transposed conv with this
                             // many real output channels; the epilogue pixel-shuffles them into the NCHW output
@@ -69,7 +71,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tcols = 32;
-    while (tcols < p.Cout) tcols <<= 1;
+    // (the epilogue reads 32-column groups: a Cout that is not a multiple of 32 needs 16 columns of slack)
+    while (tcols < p.nmma * p.Cout + ((p.Cout & 31) ? 16 : 0)) tcols <<= 1;
 
     int tile = blockIdx.x;
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -79,9 +82,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     if (tid == 0) {
         ptx::prefetch_tmap(&tma_in);
         ptx::prefetch_tmap(&tma_w);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(bfull(s), 1); ptx::mbar_init(bempty(s), 1); }
-        for (int b = 0; b < CH_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
-        ptx::mbar_init(tfull, 1);
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(bfull(s), 1); ptx::mbar_init(bempty(s), (uint32_t)p.nmma); }
+        for (int b = 0; b < CH_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), (uint32_t)p.nmma); }
+        ptx::mbar_init(tfull, (uint32_t)p.nmma);
         ptx::fence_mbar_init();
     }
     for (int c = tid; c < p.Cout; c += CH_THREADS) {
@@ -137,32 +140,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                 if (st == (uint32_t)S) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CH_MAX_STAGES; dst = sbase + ring_off; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (warp == 3 && p.nmma == 2)) {
+        // issuer mi takes k-steps mi, mi + nmma, ... (ring position advances by nmma) into its own accumulator
+        const int mi = warp >> 1, nm = p.nmma;
         const bool leader = ptx::elect_one();
         const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
         const uint32_t a_hi = ptx::desc_hi_sw128(WP * 128), b_hi = ptx::desc_hi_sw128(1024);
         const uint32_t rs16 = (uint32_t)(p.BN * WP * 128) >> 4;        // one padded halo row in 16-byte units
         const uint32_t b_lo0 = (sbase + ring_off) >> 4, b_step = (uint32_t)b_bytes >> 4;
-        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CH_MAX_STAGES, b_lo = b_lo0, acc = 0;
-        for (int c = 0; c < chunks; ++c) {
+        const uint32_t dacc = tmem_base + (uint32_t)(mi * p.Cout);
+        uint32_t st = (uint32_t)mi, par = 0, acc = 0;
+        int kbase = 0;
+        for (int c = 0; c < chunks; ++c, kbase += 9) {
             const int hb = c % CH_HALO_BUFS;
             ptx::mbar_wait(hfull(hb), (uint32_t)((c / CH_HALO_BUFS) & 1));
             const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_stride)) >> 4;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                ptx::mbar_wait(full_bar, par);
+            for (int t = (mi - kbase) & (nm - 1); t < 9; t += nm) {
+                ptx::mbar_wait(bfull((int)st), par);
                 ptx::tc_fence_after();
                 // tap (dy,dx): the halo tile read (dy+1) padded rows and (dx+1) pixels further in; the
                 // descriptor's base_offset stays 0 (swizzle phase = absolute address bits, measured)
                 const uint32_t a_lo = h_lo + (uint32_t)(p.tap_dy[t] + 1) * rs16 + (uint32_t)(p.tap_dx[t] + 1) * 8u;
+                const uint32_t b_lo = b_lo0 + st * b_step;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, acc);
+                    if (leader) ptx::mma_tf32_w(dacc, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, acc);
                     acc = 1;
                 }
-                ++st; full_bar += 8; b_lo += b_step;
-                if ((st & (CH_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
-                if (st == (uint32_t)S) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CH_MAX_STAGES; b_lo = b_lo0; }
+                // a ring group (CH_GROUP stages) is released by one commit per issuer, after its last stage of the group
+                if ((st & (CH_GROUP - 1)) + (uint32_t)nm >= (uint32_t)CH_GROUP) {
+                    if (leader) ptx::tc_commit(bempty((int)(st / CH_GROUP)));
+                }
+                st += (uint32_t)nm;
+                if (st >= (uint32_t)S) { st -= (uint32_t)S; par ^= 1; }
             }
             if (leader) ptx::tc_commit(hempty(hb));            // chunk done: its halo buffer may be refilled
             __syncwarp();
@@ -185,6 +195,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
             float v[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
             ptx::tmem_ld_wait32(v);
+            if (p.nmma == 2) {                          // + the second issuer's partial (columns Cout..)
+                float u[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.Cout, u);
+                ptx::tmem_ld_wait32(u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+            }
             if (valid) {
                 const int co_n = p.shuffle_cout, OH = 2 * p.H, OW = 2 * p.W;
                 for (int co = 0; co < co_n; ++co)
@@ -201,6 +218,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
             float v[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             ptx::tmem_ld_wait32(v);
+            if (p.nmma == 2) {
+                float u[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.Cout + c0), u);
+                ptx::tmem_ld_wait32(u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+            }
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -266,6 +290,10 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     q.tiles_y = (p.H + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
     q.bo_mode = 0;
+    {
+        static const int want = [] { const char *e = getenv("VQB_CONV_NMMA"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        q.nmma = (want == 2 && 2 * p.Cout <= 256) ? 2 : 1;       // <= 256 TMEM columns: two CTAs per SM can still allocate
+    }
     q.shuffle_cout = shuffle_cout;
     for (int t = 0; t < 9; ++t) { q.tap_w[t] = p.tap_w[t]; q.tap_dy[t] = p.tap_dy[t]; q.tap_dx[t] = p.tap_dx[t]; }
 

@@ -33,7 +33,8 @@ extern "C" int vqb_debug_read_trace(unsigned long long *dst, int n) {
 
 namespace {
 
-constexpr int RT_THREADS = 256;
+constexpr int RT_THREADS = 320;       // warps 0-3 epilogue, 4 TMA producer, 5 TMEM allocator, 6-9 MMA issuers
+constexpr int RT_MAX_ISSUERS = 4;
 constexpr int RT_MAX_STAGES = 32;     // W1 tile ring, as deep as shared memory allows
 constexpr int RT_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int RT_HALO_BUFS = 2;       // double-buffered halo tiles
@@ -48,6 +49,8 @@ struct ResTcParams {
     int stages;
     int WP;                 // halo tile width in pixels: 8 + 1 each side = 10 (see conv_halo.cu), or 16 (VQB_HALO_WP)
     int relu_out;
+    int nmma;               // GEMM1 issuer warps (1, 2 or 4): k-step i goes to issuer i % nmma, each accumulates its own
+                            // D1 partial in TMEM; epilogue 1 sums them in a fixed order (deterministic)
     int napp;               // applications of the (shared-weight) layer chained inside the kernel (residual.py:45-50);
                             // > 1 only in staged mode with tiles that hold whole images: the activation then stays
                             // in the halo buffers (borders = the conv's zero padding) and is rewritten in place
@@ -93,8 +96,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 128) trace_mark(0);                     // kernel entry
     int tcols = 32;
-    while (tcols < p.Cmid + p.C) tcols <<= 1;
-    const uint32_t d2col = (uint32_t)p.Cmid;                // D1 at column 0, D2 right after it
+    while (tcols < p.nmma * p.Cmid + p.C) tcols <<= 1;
+    const uint32_t d2col = (uint32_t)(p.nmma * p.Cmid);     // D1 partials at columns 0.., D2 right after them
 
     int tile = blockIdx.x;
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -105,17 +108,17 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::prefetch_tmap(&tma_in);
         ptx::prefetch_tmap(&tma_w1);
         ptx::prefetch_tmap(&tma_w2);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), (uint32_t)p.nmma); }
         ptx::mbar_init(w2full, 1);
-        ptx::mbar_init(d1full, 1);
+        ptx::mbar_init(d1full, (uint32_t)p.nmma);           // one commit per issuer
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
         ptx::mbar_init(actready, 4);                        // one arrival per epilogue warp
-        for (int b = 0; b < hbufs; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
+        for (int b = 0; b < hbufs; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), (uint32_t)p.nmma); }
         ptx::prefetch_tmap(&tma_out);
         ptx::fence_mbar_init();
     }
-    if (warp == 6) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
+    if (warp == 5) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -124,9 +127,10 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
 
-    // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 MMA issuer, 6 TMEM
-    // allocator.  The single-thread issuers get the HIGHER warp ids of their sub-partitions on purpose:
-    // the scheduler favours high warp ids, and the epilogue warps poll barriers for most of the kernel.
+    // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 TMEM allocator, 6.. MMA
+    // issuers.  GEMM1 has N = Cmid = 32: the tensor pipe needs ~22 cycles per MMA, one issuing warp manages
+    // one per ~135 (barrier wait + descriptor arithmetic per k-step are dependent scalar code), so the k-steps
+    // are dealt round-robin to up to four issuer warps with private accumulators.
     if (warp == 4) {
         {
             const bool leader = ptx::elect_one();       // converged warp, one issuing lane
@@ -178,17 +182,19 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp >= 6 && warp - 6 < p.nmma) {
         {
+            const int mi = warp - 6, nm = p.nmma;
             const bool leader = ptx::elect_one();       // all 32 lanes run the loop; only `leader` issues
             const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cmid);
             const uint32_t idesc2 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.C);
-            // GEMM1 issue loop: running stage pointer / parity, taps unrolled (descriptor words are
-            // constants + one add), one commit per RT_GROUP stages.
             const uint32_t a_hi = ptx::desc_hi_sw128(RT_WP * 128), b_hi = ptx::desc_hi_sw128(1024);
             const uint32_t rs16 = (uint32_t)(p.BN * RT_WP * 128) >> 4;      // one padded halo row, in 16-byte units
             const uint32_t b_lo0 = (sbase + ring_off) >> 4, b_step = (uint32_t)stage_bytes >> 4;
-            uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES, b_lo = b_lo0;
+            const uint32_t dacc = tmem_base + (uint32_t)(mi * p.Cmid);      // this issuer's D1 partial
+            // this issuer's k-steps are mi, mi + nm, ...: its ring position advances by nm (S is a multiple of 4)
+            uint32_t st = (uint32_t)mi, par = 0;
+            int kbase = 0;                              // global index of the current chunk's first k-step
             for (int app = 0; app < p.napp; ++app) {
                 const uint32_t ap = (uint32_t)(app & 1);
                 uint32_t acc = 0;
@@ -197,45 +203,49 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     ptx::mbar_wait(actready, ap ^ 1u);
                     ptx::tc_fence_after();
                 }
-                for (int c = 0; c < chunks; ++c) {
+                for (int c = 0; c < chunks; ++c, kbase += 9) {
                     const int hb = c % hbufs;
                     ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
-                    if (leader && app == 0) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
+                    if (leader && app == 0 && mi == 0) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
                     const uint32_t h_lo = (sbase + (uint32_t)(hb * halo_stride)) >> 4;
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        ptx::mbar_wait(full_bar, par);
+                    for (int t = (mi - kbase) & (nm - 1); t < 9; t += nm) {
+                        ptx::mbar_wait(full((int)st), par);
                         ptx::tc_fence_after();
                         // tap (dy,dx) = (t/3-1, t%3-1): the halo tile read (dy+1) padded rows and (dx+1) pixels
                         // further in; base_offset stays 0 (the swizzle phase comes from the absolute address)
-                        const uint32_t a_lo = h_lo + (uint32_t)(t / 3) * rs16 + (uint32_t)(t % 3) * 8u;
+                        const uint32_t t3 = ((uint32_t)t * 11u) >> 5;           // t / 3 for t < 9
+                        const uint32_t a_lo = h_lo + t3 * rs16 + ((uint32_t)t - 3u * t3) * 8u;
+                        const uint32_t b_lo = b_lo0 + st * b_step;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc1, acc);
+                            if (leader) ptx::mma_tf32_w(dacc, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc1, acc);
                             acc = 1;
                         }
-                        ++st; full_bar += 8; b_lo += b_step;
-                        if ((st & (RT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
-                        if (st == (uint32_t)S) {
-                            st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * RT_MAX_STAGES; b_lo = b_lo0;
+                        // a ring group (RT_GROUP stages) is released by one commit per issuer, after its last stage of the group
+                        if ((st & (RT_GROUP - 1)) + (uint32_t)nm >= (uint32_t)RT_GROUP) {
+                            if (leader) ptx::tc_commit(empty((int)(st / RT_GROUP)));
                         }
+                        st += (uint32_t)nm;
+                        if (st >= (uint32_t)S) { st -= (uint32_t)S; par ^= 1; }
                     }
                     if (leader && !p.staged) ptx::tc_commit(hempty(hb));     // chunk done: its halo buffer may be refilled
                     __syncwarp();
                 }
-                if (leader) { ptx::tc_commit(d1full); if (app == 0) trace_mark(8); }    // all GEMM1 MMAs issued
-                // GEMM2 once the epilogue has written relu(D1) as the A2 operand
-                if (app == 0) ptx::mbar_wait(w2full, 0);
-                ptx::mbar_wait(a2ready, ap);
-                ptx::tc_fence_after();
-                for (int a = 0; a < matoms; ++a)
+                if (leader) { ptx::tc_commit(d1full); if (app == 0 && mi == 0) trace_mark(8); }    // this issuer's GEMM1 MMAs issued
+                if (mi == 0) {
+                    // GEMM2 once the epilogue has written relu(D1) as the A2 operand
+                    if (app == 0) ptx::mbar_wait(w2full, 0);
+                    ptx::mbar_wait(a2ready, ap);
+                    ptx::tc_fence_after();
+                    for (int a = 0; a < matoms; ++a)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        if (leader)
-                            ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
-                                          ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
-                                          (a > 0 || kk > 0) ? 1u : 0u);
-                if (leader) { ptx::tc_commit(d2full); if (app == 0) trace_mark(11); }   // GEMM2 issued
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (leader)
+                                ptx::mma_tf32(tmem_base + d2col, ptx::smem_desc_sw128(sbase + a2_off + a * RT_A_BYTES + kk * 32),
+                                              ptx::smem_desc_sw128(sbase + w2_off + a * p.C * 128 + kk * 32), idesc2,
+                                              (a > 0 || kk > 0) ? 1u : 0u);
+                    if (leader) { ptx::tc_commit(d2full); if (app == 0) trace_mark(11); }   // GEMM2 issued
+                }
                 __syncwarp();
             }
         }
@@ -261,6 +271,13 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             float v[32];
             ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
             ptx::tmem_ld_wait32(v);
+            for (int m = 1; m < p.nmma; ++m) {              // + the other issuers' partials, fixed order
+                float u[32];
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(m * p.Cmid + a * 32), u);
+                ptx::tmem_ld_wait32(u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+            }
             unsigned char *arow = sm + a2_off + a * RT_A_BYTES + row * 128;
 #pragma unroll
             for (int c16 = 0; c16 < 8; ++c16) {
@@ -357,7 +374,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     if (tid == 0) trace_mark(13);                    // epilogue 2 stores issued
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 6) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, (uint32_t)tcols);
     if (tid == 128) trace_mark(14);                      // exit
 }
 
@@ -388,6 +405,11 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
         q.flags = fl ? atoi(fl) : 0;
     }
     q.napp = napp;
+    {
+        static const int want = [] { const char *e = getenv("VQB_RES_NMMA"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
+        q.nmma = want;
+        while (q.nmma > 1 && q.nmma * Cmid + C > 512) q.nmma >>= 1;      // TMEM columns: nmma D1 partials + D2
+    }
     q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
     q.BH = rt_pow2_ceil(H) < 16 ? rt_pow2_ceil(H) : 16;
     q.BN = 16 / q.BH;
