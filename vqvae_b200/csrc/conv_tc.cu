@@ -36,6 +36,7 @@ struct ConvTcParams {
     int tiles_x, tiles_y;                          // of the largest phase grid
     int in_step, out_step;
     int stages;
+    int nmma;                                      // MMA issuer warps (1 or 2), see res_tc.cu
     // blockIdx.y = phase (1 for a plain conv, stride^2 sub-pixel phases of a transposed conv)
     int OHg[4], OWg[4], out_py[4], out_px[4], ntaps[4];
     int tap_w[4][VQB_MAX_TAPS], tap_dy[4][VQB_MAX_TAPS], tap_dx[4][VQB_MAX_TAPS];
@@ -63,7 +64,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tcols = 32;
-    while (tcols < p.Cout) tcols <<= 1;
+    while (tcols < p.nmma * p.Cout + ((p.Cout & 31) ? 16 : 0)) tcols <<= 1;
 
     // tile origin
     int tile = blockIdx.x;
@@ -74,8 +75,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
     if (tid == 0) {
         ptx::prefetch_tmap(&tma_in);
         ptx::prefetch_tmap(&tma_w);
-        for (int s = 0; s < CT_STAGES; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
-        ptx::mbar_init(tfull, 1);
+        for (int s = 0; s < CT_STAGES; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), (uint32_t)p.nmma); }
+        ptx::mbar_init(tfull, (uint32_t)p.nmma);
         ptx::fence_mbar_init();
     }
     for (int c = tid; c < p.Cout; c += CT_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
@@ -110,23 +111,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
                 if (st == (uint32_t)CT_STAGES) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CT_MAX_STAGES; dst = sbase; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (warp == 3 && p.nmma == 2)) {
+        // issuer mi takes k-steps mi, mi + nmma, ... into its own accumulator (columns mi * Cout ..)
+        const int mi = warp >> 1, nm = p.nmma;
         const bool leader = ptx::elect_one();
         const uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cout);
         const uint32_t d_hi = ptx::desc_hi_sw128(1024);
         const uint32_t a_lo0 = sbase >> 4, step16 = (uint32_t)stage_bytes >> 4;
-        uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * CT_MAX_STAGES, a_lo = a_lo0, acc = 0;
-        for (int i = 0; i < ksteps; ++i) {
-            ptx::mbar_wait(full_bar, par);
+        const uint32_t dacc = tmem_base + (uint32_t)(mi * p.Cout);
+        uint32_t st = (uint32_t)mi, par = 0, acc = 0;
+        for (int i = mi; i < ksteps; i += nm) {
+            ptx::mbar_wait(full((int)st), par);
             ptx::tc_fence_after();
+            const uint32_t a_lo = a_lo0 + st * step16;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                if (leader) ptx::mma_tf32_w(tmem_base, a_lo + 2u * kk, d_hi, a_lo + (A_BYTES >> 4) + 2u * kk, d_hi, idesc, acc);
+                if (leader) ptx::mma_tf32_w(dacc, a_lo + 2u * kk, d_hi, a_lo + (A_BYTES >> 4) + 2u * kk, d_hi, idesc, acc);
                 acc = 1;
             }
-            ++st; full_bar += 8; a_lo += step16;
-            if ((st & (CT_GROUP - 1)) == 0) { if (leader) ptx::tc_commit(empty_bar); empty_bar += 8; }
-            if (st == (uint32_t)CT_STAGES) { st = 0; par ^= 1; full_bar = bars; empty_bar = bars + 8u * CT_MAX_STAGES; a_lo = a_lo0; }
+            if ((st & (CT_GROUP - 1)) + (uint32_t)nm >= (uint32_t)CT_GROUP) {
+                if (leader) ptx::tc_commit(empty((int)(st / CT_GROUP)));
+            }
+            st += (uint32_t)nm;
+            if (st >= (uint32_t)CT_STAGES) { st -= (uint32_t)CT_STAGES; par ^= 1; }
         }
         if (leader) ptx::tc_commit(tfull);
         __syncwarp();
@@ -148,6 +155,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
             if (ksteps > 0) {
                 ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 ptx::tmem_ld_wait32(v);
+                if (p.nmma == 2 && ksteps >= 2) {          // + the second issuer's partial
+                    float u[32];
+                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.Cout + c0), u);
+                    ptx::tmem_ld_wait32(u);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -255,6 +269,10 @@ int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_t
     else stages -= stages % CT_GROUP;             // a reused ring must hold whole commit groups
     if (stages < 1) stages = 1;
     q.stages = stages;
+    {
+        static const int want = [] { const char *e = getenv("VQB_CONV_NMMA"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        q.nmma = (want == 2 && 2 * p.Cout <= 256 && stages >= 2 && (stages % 2 == 0 || stages >= maxk)) ? 2 : 1;
+    }
     const int smem = stages * stage_bytes + 192 + p.Cout * 4 + 1024;
     static int attr_max = 0;
     if (smem > attr_max) {
