@@ -266,7 +266,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         // ---- epilogue 1: relu(D1) -> A2 operand in shared memory ----
         ptx::mbar_wait_sleep(d1full, ap);
         ptx::tc_fence_after();
-        if (tid == 0 && app == 0) trace_mark(9);                 // GEMM1 complete (epilogue sees D1)
+        if (tid == 0 && app < 2) trace_mark(9 + 16 * app);       // GEMM1 complete (epilogue sees D1)
         for (int a = 0; a < matoms; ++a) {
             float v[32];
             ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
@@ -290,12 +290,12 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a2ready);
-        if (tid == 0 && app == 0) trace_mark(10);                // A2 written
+        if (tid == 0 && app < 2) trace_mark(10 + 16 * app);      // A2 written
 
         // ---- epilogue 2: D2 + skip -> ReLU -> next application's input / NHWC store ----
         ptx::mbar_wait_sleep(d2full, ap, 64);
         ptx::tc_fence_after();
-        if (tid == 0 && app == 0) trace_mark(12);                // GEMM2 complete
+        if (tid == 0 && app < 2) trace_mark(12 + 16 * app);      // GEMM2 complete
         if (!last) {
             // chained application (staged mode, whole images per tile): r_{a+1} = act(r_a + D2) replaces r_a in
             // the halo buffers, same thread, same address; pixels outside the image stay zero (= conv padding)
@@ -320,6 +320,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(actready);
+            if (tid == 0 && app == 0) trace_mark(15);            // activation rewritten in place
             continue;
         }
         if (p.staged) {
@@ -409,6 +410,8 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
         static const int want = [] { const char *e = getenv("VQB_RES_NMMA"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
         q.nmma = want;
         while (q.nmma > 1 && q.nmma * Cmid + C > 512) q.nmma >>= 1;      // TMEM columns: nmma D1 partials + D2
+        // the k-steps of every application must deal out the same way (fused == separate launches, bit for bit)
+        while (q.nmma > 1 && (9 * (C / 32)) % q.nmma != 0) q.nmma >>= 1;
     }
     q.skip = r; q.out = out; q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
     q.BH = rt_pow2_ceil(H) < 16 ? rt_pow2_ceil(H) : 16;
