@@ -129,6 +129,17 @@ int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, 
                        int64_t *idx, float *zq, double *sse, int32_t *hist,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Deferred variant: identical outputs, except that `sse` is only final after
+ * vqb_vq_reduce_sse_f32 has run on the same workspace (stream-ordered after this call).
+ * The per-CTA SSE partials stay in the workspace, so the tiny reduction -- and the scalar
+ * finisher that needs it -- can run on a side stream while the decoder consumes zq
+ * (vqvae.py:36 does not depend on the loss terms of quantizer.py:63-64).              */
+int vqb_vq_forward_deferred_f32(const float *z, const float *codebook, int64_t N, int K, int D,
+                                int64_t *idx, float *zq, double *sse, int32_t *hist,
+                                void *workspace, size_t workspace_bytes, void *stream);
+int vqb_vq_reduce_sse_f32(const void *workspace, int64_t N, int K, int D, double *sse,
+                          void *stream);
+
 /* Kernel choice of vqb_vq_forward_f32: 0 = auto (tcgen05 kernel when D == 64, else the
  * exact FFMA kernel), 1 = always the FFMA kernel, 2 = require the tcgen05 kernel.  Both
  * produce bit-identical idx / zq; the switch exists for tests and benchmarks.        */

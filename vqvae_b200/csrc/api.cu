@@ -9,8 +9,10 @@ int launch_vq_exact(const float *z, const float *E, long long N, int K, int D, l
 
 size_t vq_tc_workspace_bytes(int K);
 bool vq_tc_supported(long long N, int K, int D);
+size_t vq_ws_marker_offset(int K);
+int launch_vq_reduce_sse(const void *ws, int K, double *sse, cudaStream_t s);
 int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
-                 int *hist, void *ws, float *dbg, cudaStream_t s);
+                 int *hist, void *ws, float *dbg, int defer, cudaStream_t s);
 
 int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
                         int Cout, int relu, cudaStream_t s);
@@ -188,13 +190,39 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
 extern "C" size_t vqb_vq_workspace_bytes(int64_t N, int K, int D) {
     (void)N; (void)D;
     if (K <= 0) return 0;
+    return vq_ws_marker_offset(K) + 256;
+}
+
+// [exact / tcgen05 kernel workspace (whichever is larger)][256 B: deferred-reduction marker]
+size_t vq_ws_marker_offset(int K) {
     const size_t a = vq_exact_workspace_bytes(K), b = vq_tc_workspace_bytes(K);
-    return a > b ? a : b;
+    return ((a > b ? a : b) + 255) / 256 * 256;
+}
+
+static int vq_forward_impl(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx, float *zq,
+                           double *sse, int32_t *hist, void *workspace, size_t workspace_bytes, int defer,
+                           void *stream);
+
+extern "C" int vqb_vq_forward_deferred_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
+                                           float *zq, double *sse, int32_t *hist, void *workspace,
+                                           size_t workspace_bytes, void *stream) {
+    return vq_forward_impl(z, codebook, N, K, D, idx, zq, sse, hist, workspace, workspace_bytes, 1, stream);
+}
+
+extern "C" int vqb_vq_reduce_sse_f32(const void *workspace, int64_t N, int K, int D, double *sse, void *stream) {
+    if (!workspace || !sse || N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
+    return launch_vq_reduce_sse(workspace, K, sse, (cudaStream_t)stream);
 }
 
 extern "C" int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
                                   float *zq, double *sse, int32_t *hist, void *workspace,
                                   size_t workspace_bytes, void *stream) {
+    return vq_forward_impl(z, codebook, N, K, D, idx, zq, sse, hist, workspace, workspace_bytes, 0, stream);
+}
+
+static int vq_forward_impl(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx, float *zq,
+                           double *sse, int32_t *hist, void *workspace, size_t workspace_bytes, int defer,
+                           void *stream) {
     if (!z || !codebook || !idx || !zq || !sse || !hist || !workspace) return VQB_ERR_BAD_ARG;
     if (N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
     if (D % 4 != 0) return VQB_ERR_UNSUPPORTED;
@@ -206,9 +234,13 @@ extern "C" int vqb_vq_forward_f32(const float *z, const float *codebook, int64_t
     if (g_vq_kernel == 2 && !tc_ok) return VQB_ERR_UNSUPPORTED;
     if (tc_ok && g_vq_kernel != 1)
         return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
-                            nullptr, (cudaStream_t)stream);
-    return launch_vq_exact(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
-                           (cudaStream_t)stream);
+                            nullptr, defer, (cudaStream_t)stream);
+    const int rc = launch_vq_exact(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
+                                   (cudaStream_t)stream);
+    if (rc || !defer) return rc;
+    // sse is final: nothing pending for vqb_vq_reduce_sse_f32
+    return vqb_cuda_status(cudaMemsetAsync(reinterpret_cast<unsigned char *>(workspace) + vq_ws_marker_offset(K), 0, 4,
+                                           (cudaStream_t)stream));
 }
 
 extern "C" int vqb_debug_vq_scores_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
@@ -217,7 +249,7 @@ extern "C" int vqb_debug_vq_scores_f32(const float *z, const float *codebook, in
     if (!z || !codebook || !idx || !zq || !sse || !hist || !workspace || !scores) return VQB_ERR_BAD_ARG;
     if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
     if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
-    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores,
+    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores, 0,
                         (cudaStream_t)stream);
 }
 

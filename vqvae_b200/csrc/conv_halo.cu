@@ -42,7 +42,7 @@ struct ConvHaloParams {
     int tap_w[9], tap_dy[9], tap_dx[9];
 };
 
-__global__ void __launch_bounds__(CH_THREADS)
+__global__ void __launch_bounds__(CH_THREADS, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
                  const ConvHaloParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -79,14 +79,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
     const int ty = tile % p.tiles_y; tile /= p.tiles_y;
     const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = tile * p.BN;
 
-    if (tid == 0) {
-        ptx::prefetch_tmap(&tma_in);
-        ptx::prefetch_tmap(&tma_w);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(bfull(s), 1); ptx::mbar_init(bempty(s), (uint32_t)p.nmma); }
-        for (int b = 0; b < CH_HALO_BUFS; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), (uint32_t)p.nmma); }
-        ptx::mbar_init(tfull, (uint32_t)p.nmma);
-        ptx::fence_mbar_init();
-    }
+    if (tid < S) { ptx::mbar_init(bfull(tid), 1); ptx::mbar_init(bempty(tid), (uint32_t)p.nmma); }     // init spread over threads
+    if (tid >= 64 && tid < 64 + CH_HALO_BUFS) { ptx::mbar_init(hfull(tid - 64), 1); ptx::mbar_init(hempty(tid - 64), (uint32_t)p.nmma); }
+    if (tid == 96) ptx::mbar_init(tfull, (uint32_t)p.nmma);
+    if (tid == 128) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w); }
+    ptx::fence_mbar_init();
     for (int c = tid; c < p.Cout; c += CH_THREADS) {
         if (p.shuffle_cout > 0) bias_s[c] = (p.bias && c < 4 * p.shuffle_cout) ? __ldg(p.bias + c % p.shuffle_cout) : 0.f;
         else bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
@@ -213,33 +210,60 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_consta
                         *reinterpret_cast<float2 *>(p.out + (((long long)n * co_n + co) * OH + 2 * gy + py) * OW + 2 * gx) = o;
                     }
             }
-        } else
-        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-            float v[32];
-            ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            ptx::tmem_ld_wait32(v);
-            if (p.nmma == 2) {
-                float u[32];
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.Cout + c0), u);
-                ptx::tmem_ld_wait32(u);
+        } else {
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const bool two = p.nmma == 2, have = true;
+            auto emit = [&](float (&v)[32], int c0) {
+                if (!have) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
-            }
-            if (valid) {
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (c0 + i < p.Cout) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
-                        float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
-                        if (p.skip) {
-                            const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
-                            o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                    for (int i = 0; i < 32; i += 4) {
+                        if (c0 + i < p.Cout) {             // Cout % 16 == 0: whole float4s
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
+                            float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                            if (p.skip) {
+                                const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
+                                o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                            }
+                            if (p.relu) {
+                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                            }
+                            *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
                         }
-                        if (p.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
                     }
+                }
+            };
+            // the TMEM loads of the next 32 columns travel while the current ones are stored (a tcgen05.ld round
+            // trip is ~0.2 us); three register arrays: the partial `u` is folded into its `v` before the next load
+            float va[32], vb[32], u[32];
+            auto load = [&](float (&v)[32], int c0) {
+                if (have) {
+                    ptx::tmem_ld32(trow + (uint32_t)c0, v);
+                    if (two) ptx::tmem_ld32(trow + (uint32_t)(p.Cout + c0), u);
+                }
+            };
+            auto wait = [&](float (&v)[32]) {
+                if (have) {
+                    ptx::tmem_ld_wait32(v);
+                    if (two) {
+                        ptx::tmem_ld_wait32(u);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);      // + the second issuer's partial
+                    }
+                }
+            };
+            load(va, 0);
+            for (int c0 = 0; c0 < p.Cout; c0 += 64) {
+                wait(va);
+                if (c0 + 32 < p.Cout) load(vb, c0 + 32);
+                emit(va, c0);
+                if (c0 + 32 < p.Cout) {
+                    wait(vb);
+                    if (c0 + 64 < p.Cout) load(va, c0 + 64);
+                    emit(vb, c0 + 32);
                 }
             }
         }

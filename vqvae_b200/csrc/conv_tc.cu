@@ -44,7 +44,7 @@ struct ConvTcParams {
     int relu;
 };
 
-__global__ void __launch_bounds__(CT_THREADS)
+__global__ void __launch_bounds__(CT_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
                const ConvTcParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -72,13 +72,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
     const int ty = tile % p.tiles_y; tile /= p.tiles_y;
     const int gx0 = tx * p.BW, gy0 = ty * p.BH, n0 = tile * p.BN;
 
-    if (tid == 0) {
-        ptx::prefetch_tmap(&tma_in);
-        ptx::prefetch_tmap(&tma_w);
-        for (int s = 0; s < CT_STAGES; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), (uint32_t)p.nmma); }
-        ptx::mbar_init(tfull, (uint32_t)p.nmma);
-        ptx::fence_mbar_init();
-    }
+    if (tid < CT_STAGES) { ptx::mbar_init(full(tid), 1); ptx::mbar_init(empty(tid), (uint32_t)p.nmma); }      // init spread over threads
+    if (tid == 32) ptx::mbar_init(tfull, (uint32_t)p.nmma);
+    if (tid == 64) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w); }
+    ptx::fence_mbar_init();
     for (int c = tid; c < p.Cout; c += CT_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
     if (warp == 2) ptx::tmem_alloc(sbase + CT_STAGES * stage_bytes + 176, (uint32_t)tcols);
     ptx::tc_fence_before();
@@ -150,37 +147,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant
             ptx::mbar_wait(tfull, 0);
             ptx::tc_fence_after();
         }
-        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-            float v[32];
-            if (ksteps > 0) {
-                ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                ptx::tmem_ld_wait32(v);
-                if (p.nmma == 2 && ksteps >= 2) {          // + the second issuer's partial
-                    float u[32];
-                    ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.Cout + c0), u);
-                    ptx::tmem_ld_wait32(u);
+        {
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const bool two = (p.nmma == 2 && ksteps >= 2), have = (ksteps > 0);
+            auto emit = [&](float (&v)[32], int c0) {
+                if (!have) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
-            } else {
+                if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            }
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (c0 + i < p.Cout) {             // Cout % 16 == 0: whole float4s
-                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
-                        float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
-                        if (p.skip) {
-                            const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
-                            o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                    for (int i = 0; i < 32; i += 4) {
+                        if (c0 + i < p.Cout) {             // Cout % 16 == 0: whole float4s
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
+                            float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                            if (p.skip) {
+                                const float4 sk = __ldg(reinterpret_cast<const float4 *>(p.skip + ob + c0 + i));
+                                o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                            }
+                            if (p.relu) {
+                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                            }
+                            *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
                         }
-                        if (p.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        *reinterpret_cast<float4 *>(p.out + ob + c0 + i) = o;
                     }
+                }
+            };
+            // the TMEM loads of the next 32 columns travel while the current ones are stored (a tcgen05.ld round
+            // trip is ~0.2 us); three register arrays: the partial `u` is folded into its `v` before the next load
+            float va[32], vb[32], u[32];
+            auto load = [&](float (&v)[32], int c0) {
+                if (have) {
+                    ptx::tmem_ld32(trow + (uint32_t)c0, v);
+                    if (two) ptx::tmem_ld32(trow + (uint32_t)(p.Cout + c0), u);
+                }
+            };
+            auto wait = [&](float (&v)[32]) {
+                if (have) {
+                    ptx::tmem_ld_wait32(v);
+                    if (two) {
+                        ptx::tmem_ld_wait32(u);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);      // + the second issuer's partial
+                    }
+                }
+            };
+            load(va, 0);
+            for (int c0 = 0; c0 < p.Cout; c0 += 64) {
+                wait(va);
+                if (c0 + 32 < p.Cout) load(vb, c0 + 32);
+                emit(va, c0);
+                if (c0 + 32 < p.Cout) {
+                    wait(vb);
+                    if (c0 + 64 < p.Cout) load(va, c0 + 64);
+                    emit(vb, c0 + 32);
                 }
             }
         }

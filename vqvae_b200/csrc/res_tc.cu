@@ -104,20 +104,19 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     const int ty = tile % p.tiles_y; tile /= p.tiles_y;
     const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = tile * p.BN;
 
-    if (tid == 0) {
-        ptx::prefetch_tmap(&tma_in);
-        ptx::prefetch_tmap(&tma_w1);
-        ptx::prefetch_tmap(&tma_w2);
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), (uint32_t)p.nmma); }
+    // barrier init spread over the threads (one thread initialising ~80 barriers cost 0.7 us of every launch)
+    if (tid < S) { ptx::mbar_init(full(tid), 1); ptx::mbar_init(empty(tid), (uint32_t)p.nmma); }
+    if (tid >= 64 && tid < 64 + hbufs) { ptx::mbar_init(hfull(tid - 64), 1); ptx::mbar_init(hempty(tid - 64), (uint32_t)p.nmma); }
+    if (tid == 96) {
         ptx::mbar_init(w2full, 1);
         ptx::mbar_init(d1full, (uint32_t)p.nmma);           // one commit per issuer
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
         ptx::mbar_init(actready, 4);                        // one arrival per epilogue warp
-        for (int b = 0; b < hbufs; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), (uint32_t)p.nmma); }
-        ptx::prefetch_tmap(&tma_out);
-        ptx::fence_mbar_init();
     }
+    if (tid == 128) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w1); }
+    if (tid == 160) { ptx::prefetch_tmap(&tma_w2); ptx::prefetch_tmap(&tma_out); }
+    ptx::fence_mbar_init();
     if (warp == 5) ptx::tmem_alloc(sbase + bar_off + RT_MISC, (uint32_t)tcols);
     ptx::tc_fence_before();
     __syncthreads();
@@ -269,14 +268,25 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         if (tid == 0 && app < 2) trace_mark(9 + 16 * app);       // GEMM1 complete (epilogue sees D1)
         for (int a = 0; a < matoms; ++a) {
             float v[32];
-            ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
-            ptx::tmem_ld_wait32(v);
-            for (int m = 1; m < p.nmma; ++m) {              // + the other issuers' partials, fixed order
-                float u[32];
-                ptx::tmem_ld32(lane_taddr + (uint32_t)(m * p.Cmid + a * 32), u);
-                ptx::tmem_ld_wait32(u);
+            if (p.nmma == 4) {                              // all four partials in flight, then one fixed-order sum
+                float u1[32], u2[32], u3[32];
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(p.Cmid + a * 32), u1);
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(2 * p.Cmid + a * 32), u2);
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(3 * p.Cmid + a * 32), u3);
+                ptx::tmem_ld_wait32(v); ptx::tmem_ld_wait32(u1); ptx::tmem_ld_wait32(u2); ptx::tmem_ld_wait32(u3);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(__fadd_rn(__fadd_rn(v[i], u1[i]), u2[i]), u3[i]);
+            } else {
+                ptx::tmem_ld32(lane_taddr + (uint32_t)(a * 32), v);
+                ptx::tmem_ld_wait32(v);
+                for (int m = 1; m < p.nmma; ++m) {              // + the other issuers' partials, fixed order
+                    float u[32];
+                    ptx::tmem_ld32(lane_taddr + (uint32_t)(m * p.Cmid + a * 32), u);
+                    ptx::tmem_ld_wait32(u);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], u[i]);
+                }
             }
             unsigned char *arow = sm + a2_off + a * RT_A_BYTES + row * 128;
 #pragma unroll
@@ -299,10 +309,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         if (!last) {
             // chained application (staged mode, whole images per tile): r_{a+1} = act(r_a + D2) replaces r_a in
             // the halo buffers, same thread, same address; pixels outside the image stay zero (= conv padding)
-            for (int c0 = 0; c0 < p.C; c0 += 32) {
-                float v[32];
-                ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
-                ptx::tmem_ld_wait32(v);
+            auto rewrite = [&](const float (&v)[32], int c0) {
                 unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
 #pragma unroll
                 for (int c16 = 0; c16 < 8; ++c16) {
@@ -314,6 +321,20 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     }
                     if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
                     *ptr = o;
+                }
+            };
+            // two TMEM loads in flight: the next 32 columns travel while these are added and written
+            // (a tcgen05.ld round trip is ~0.2 us; four in sequence were half of this phase)
+            float va[32], vb[32];
+            ptx::tmem_ld32(lane_taddr + d2col, va);
+            for (int c0 = 0; c0 < p.C; c0 += 64) {
+                ptx::tmem_ld_wait32(va);
+                if (c0 + 32 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 32), vb);
+                rewrite(va, c0);
+                if (c0 + 32 < p.C) {
+                    ptx::tmem_ld_wait32(vb);
+                    if (c0 + 64 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 64), va);
+                    rewrite(vb, c0 + 32);
                 }
             }
             ptx::fence_proxy_async();
@@ -327,10 +348,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             // skip = centre tap of the resident halo tiles; output tile staged in shared memory (over the
             // W1 ring + A2 + W2, all dead once GEMM2 has completed) in MMA row order and TMA-stored:
             // no global skip loads, no scattered 16-byte stores.
-            for (int c0 = 0; c0 < p.C; c0 += 32) {
-                float v[32];
-                ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c0, v);
-                ptx::tmem_ld_wait32(v);
+            auto stage = [&](const float (&v)[32], int c0) {
                 const unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
                 unsigned char *orow = sm + ring_off + (c0 >> 5) * RT_A_BYTES + row * 128;
 #pragma unroll
@@ -341,6 +359,18 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
                     *reinterpret_cast<float4 *>(orow + ((c16 ^ (row & 7)) << 4)) = o;
+                }
+            };
+            float va[32], vb[32];
+            ptx::tmem_ld32(lane_taddr + d2col, va);
+            for (int c0 = 0; c0 < p.C; c0 += 64) {
+                ptx::tmem_ld_wait32(va);
+                if (c0 + 32 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 32), vb);
+                stage(va, c0);
+                if (c0 + 32 < p.C) {
+                    ptx::tmem_ld_wait32(vb);
+                    if (c0 + 64 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 64), va);
+                    stage(vb, c0 + 32);
                 }
             }
             ptx::fence_proxy_async();

@@ -93,6 +93,7 @@ struct VqTcParams {
     int K, nchunks;
     long long *idx;
     double *partials;
+    unsigned *pending;     // number of SSE partials this launch leaves in `partials` (read by vqb_vq_reduce_sse_f32)
     int *hist;
     float *dbg;            // optional (N, nchunks*256) raw approximate scores
     int flags;             // perf-experiment knobs (env VQB_TC_FLAGS), 0 in production
@@ -615,6 +616,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             double s = 0.0;
             for (int w = 0; w < 8; ++w) s += red[w];
             p.partials[blockIdx.x] = s;
+            if (blockIdx.x == 0) *p.pending = gridDim.x;
         }
         if (smem_hist)
             for (int k = et; k < p.K; k += 256) {
@@ -637,8 +639,12 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void vq_tc_sum_partials(const double *__restrict__ partials, int n, double *__restrict__ out) {
+// n < 0: the count is read from *pending (deferred reduction; 0 = sse is already final)
+__global__ void vq_tc_sum_partials(const double *__restrict__ partials, int n, const unsigned *__restrict__ pending,
+                                   double *__restrict__ out) {
     __shared__ double sh[256];
+    if (n < 0) n = (int)*pending;
+    if (n <= 0) return;
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
     sh[threadIdx.x] = s;
@@ -664,8 +670,21 @@ bool vq_tc_supported(long long N, int K, int D) {
     return D == DD && N >= 1 && N < (1LL << 31) && K >= 1 && K <= (1 << 20);
 }
 
+// the deferred-reduction marker lives behind both kernels' workspace layouts
+size_t vq_ws_marker_offset(int K);
+
+int launch_vq_reduce_sse(const void *ws, int K, double *sse, cudaStream_t s) {
+    const int Kpad = (K + CN - 1) / CN * CN;
+    const unsigned char *w = reinterpret_cast<const unsigned char *>(ws);
+    const double *partials = reinterpret_cast<const double *>(w + align256((size_t)Kpad * 4) + 256);
+    vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, -1, reinterpret_cast<const unsigned *>(w + vq_ws_marker_offset(K)), sse);
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}
+
+// defer != 0: the SSE partials stay in the workspace (vqb_vq_reduce_sse_f32 sums them later, e.g. on a side stream)
 int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
-                 int *hist, void *ws, float *dbg, cudaStream_t s) {
+                 int *hist, void *ws, float *dbg, int defer, cudaStream_t s) {
     if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
     const int nchunks = (K + CN - 1) / CN;
     const int Kpad = nchunks * CN;
@@ -714,6 +733,7 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
     p.idx = idx; p.partials = partials; p.hist = hist; p.dbg = dbg;
+    p.pending = reinterpret_cast<unsigned *>(w + vq_ws_marker_offset(K));
     {
         const char *fl = getenv("VQB_TC_FLAGS");
         p.flags = fl ? atoi(fl) : 0;
@@ -725,7 +745,7 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     }
     if (dbg) vq_tc_kernel<true><<<grid, NTHREADS, SMEM_ALLOC, s>>>(tmz, tme, tmq, p);
     else if (cudaError_t le = vqb_launch(vq_tc_kernel<false>, dim3((unsigned)grid), dim3(NTHREADS), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)) return (int)le;
-    vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, sse);
-    VQB_COUNT_LAUNCH(nlaunch);
+    if (!defer) vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, grid, nullptr, sse);
+    VQB_COUNT_LAUNCH(defer ? nlaunch - 1 : nlaunch);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -323,26 +323,25 @@ class VQVAE(nn.Module):
         vq = self.vector_quantization
         D = vq.e_dim
         group = self.process_group
-        if group is not None and torch.distributed.get_world_size(group) > 1:
-            # batch-sharded: the decoder does not depend on the two cross-sample scalars, so their tiny
-            # all-reduce + finisher run on a side stream and overlap the decoder; fork/join
-            # with events, so the whole forward stays capturable in one CUDA graph.
-            idx, zq, sse, hist = ops.vq_forward(z_e.view(-1, D), vq._codebook())
-            main = torch.cuda.current_stream()
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream()
-            side = self._side_stream
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                embedding_loss, perplexity = vq._scalars(sse, hist, z_e.shape[0] * H * W, group)
-                if not torch.cuda.is_current_stream_capturing():
-                    for t in (sse, hist, embedding_loss, perplexity):
-                        t.record_stream(side)
-            x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
-            main.wait_stream(side)
-        else:
-            embedding_loss, zq, perplexity, idx = vq._quantize_rows(z_e.view(-1, D))
-            x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
+        # The decoder does not depend on the loss / perplexity scalars (vqvae.py:36 vs quantizer.py:63-71), so
+        # the SSE reduction, the batch-sharded all-reduce and the scalar finisher run on a side
+        # stream and overlap the decoder; fork/join with events, so the whole forward stays capturable in one
+        # CUDA graph.
+        n_rows = z_e.shape[0] * H * W
+        idx, zq, sse, hist, ws = ops.vq_forward(z_e.view(-1, D), vq._codebook(), defer=True)
+        main = torch.cuda.current_stream()
+        if self._side_stream is None or self._side_stream.device != z_e.device:
+            self._side_stream = torch.cuda.Stream(device=z_e.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.vq_reduce_sse(ws, n_rows, vq.n_e, D, sse)
+            embedding_loss, perplexity = vq._scalars(sse, hist, n_rows, group)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (ws, sse, hist, embedding_loss, perplexity):
+                    t.record_stream(side)
+        x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
+        main.wait_stream(side)
         self.last_min_encoding_indices = idx.view(-1, 1)
         if verbose:                                                          # :38-42 (Q8)
             print('original data shape:', x.shape)

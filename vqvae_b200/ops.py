@@ -128,9 +128,10 @@ def residual_stack(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, n_layers, preci
     return out
 
 
-def vq_forward(z_rows, codebook):
+def vq_forward(z_rows, codebook, defer=False):
     """Fused VectorQuantizer core on (N,D) rows -> (idx int64 (N,), zq (N,D), sse f64 (1,),
-    hist int32 (K,))."""
+    hist int32 (K,)).  defer=True (vqb_vq_forward_deferred_f32) additionally returns the workspace:
+    `sse` is final only after vq_reduce_sse(ws, ...) has run (e.g. on a side stream)."""
     _require_cuda(z_rows, "z")
     N, D = z_rows.shape
     K = codebook.shape[0]
@@ -142,11 +143,18 @@ def vq_forward(z_rows, codebook):
     ws_bytes = lib().vqb_vq_workspace_bytes(N, K, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     span = _Span(f"vq N={N} K={K} D={D}")
-    check(lib().vqb_vq_forward_f32(z_rows.data_ptr(), codebook.data_ptr(), N, K, D, idx.data_ptr(),
-                                   zq.data_ptr(), sse.data_ptr(), hist.data_ptr(), ws.data_ptr(),
-                                   ws_bytes, _stream()), "vq_forward")
+    fn = lib().vqb_vq_forward_deferred_f32 if defer else lib().vqb_vq_forward_f32
+    check(fn(z_rows.data_ptr(), codebook.data_ptr(), N, K, D, idx.data_ptr(), zq.data_ptr(), sse.data_ptr(),
+             hist.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vq_forward")
     span.done()
+    if defer:
+        return idx, zq, sse, hist, ws
     return idx, zq, sse, hist
+
+
+def vq_reduce_sse(ws, N, K, D, sse):
+    """Completes `sse` after vq_forward(..., defer=True) (vqb_vq_reduce_sse_f32), on the current stream."""
+    check(lib().vqb_vq_reduce_sse_f32(ws.data_ptr(), N, K, D, sse.data_ptr(), _stream()), "vq_reduce_sse")
 
 
 def vq_finish(sse, hist, N, K, D, beta):
