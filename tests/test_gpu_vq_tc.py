@@ -101,7 +101,7 @@ def test_tc_kernel_large_n_matches_exact_kernel(K, kind):
     assert np.array_equal(i_t[:4096], o["idx"])
 
 
-@pytest.mark.parametrize("N,K,D,kernel", [(5000, 512, 64, 0), (777, 1000, 64, 0), (640, 512, 64, 1), (300, 96, 32, 0)])
+@pytest.mark.parametrize("N,K,D,kernel", [(5000, 512, 64, "auto"), (777, 1000, 64, "auto"), (640, 512, 64, "exact"), (300, 96, 32, "auto")])
 def test_deferred_sse_reduction(N, K, D, kernel):
     """vqb_vq_forward_deferred_f32 + vqb_vq_reduce_sse_f32 (the reduction may run later / on a side stream)
     give exactly the outputs of vqb_vq_forward_f32, on the tcgen05 kernel and on the exact FFMA kernel."""
@@ -120,6 +120,6 @@ def test_deferred_sse_reduction(N, K, D, kernel):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
     finally:
-        ops.set_vq_kernel(0)
+        ops.set_vq_kernel("auto")
     assert torch.equal(i0, i1) and torch.equal(q0, q1) and torch.equal(h0, h1)
     assert s0.item() == s1.item() and s0.item() > 0
