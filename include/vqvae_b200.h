@@ -186,6 +186,11 @@ int vqb_debug_read_cta_times(unsigned long long *dst, int n);
 int vqb_nchw_to_nhwc_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);
 int vqb_nhwc_to_nchw_f32(const float *in, float *out, int B, int C, int H, int W, void *stream);
 
+/* Stream-ordered copy used by the host-buffer streaming front end (vqvae_b200.HostPipeline):
+ * kind 1 = host -> device, 2 = device -> host, 3 = device -> device.  Host buffers should be
+ * pinned (the copy is only asynchronous then).                                          */
+int vqb_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

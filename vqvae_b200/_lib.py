@@ -28,6 +28,7 @@ SIGNATURES = {
     "vqb_vq_workspace_bytes": (_sz, [_i64, _i, _i]),
     "vqb_vq_forward_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vqb_vq_forward_deferred_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vqb_memcpy_async": (_i, [_vp, _vp, _sz, _i, _vp]),
     "vqb_vq_reduce_sse_f32": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "vqb_vq_finish_f32": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp]),
     "vqb_onehot_f32": (_i, [_vp, _i64, _i, _vp, _vp]),

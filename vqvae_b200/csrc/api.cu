@@ -294,3 +294,18 @@ extern "C" int vqb_residual_stack_f32(const float *r, const float *w1_packed, co
     }
     return 0;
 }
+
+// Thin stream-ordered copy for the host-buffer front end (vqvae_b200/pipeline.py): one ctypes call instead of
+// a torch stream context + Tensor.copy_ per transfer (the Python overhead per step was larger than the kernels).
+extern "C" int vqb_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream) {
+    if (!dst || !src) return VQB_ERR_BAD_ARG;
+    if (bytes == 0) return 0;
+    cudaMemcpyKind k;
+    switch (kind) {
+        case 1: k = cudaMemcpyHostToDevice; break;
+        case 2: k = cudaMemcpyDeviceToHost; break;
+        case 3: k = cudaMemcpyDeviceToDevice; break;
+        default: return VQB_ERR_BAD_ARG;
+    }
+    return vqb_cuda_status(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+}
