@@ -1,0 +1,32 @@
+"""Diagnostic: HostPipeline throughput, torch copies vs raw stream-ordered copies."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vqvae_b200
+from oracle import weights
+sd = weights.make_state_dict(128, 32, 2, 512, 64, seed=5)
+m = vqvae_b200.VQVAE(128, 32, 2, 512, 64, 0.25)
+m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+vqvae_b200.set_precision("tf32")
+m = m.cuda().eval()
+B = 256
+hosts = [torch.from_numpy(weights.make_images(B, 32, seed=1 + i)).pin_memory() for i in range(3)]
+for raw in (False, True):
+    pipe = vqvae_b200.HostPipeline(m, (B, 3, 32, 32), depth=3, raw_copies=raw)
+    acc = [0.0]
+    def consume(r): acc[0] += float(r.loss)
+    pipe.run((hosts[i % 3] for i in range(12)), consume)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        t0 = time.perf_counter()
+        pipe.run((hosts[i % 3] for i in range(200)), consume)
+        dt = time.perf_counter() - t0
+        print(f"raw={raw} MEMCPY_RT={os.environ.get('VQB_MEMCPY_RUNTIME','0')}: {dt/200*1e3:.3f} ms/step  {200*B/dt/1e6:.3f} M img/s")
+    # host-side cost of push alone (GPU idle): time 50 pushes then drain
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(3): pipe.push(hosts[i])
+    t1 = time.perf_counter()
+    pipe.drain()
+    print(f"   3 pushes took {(t1-t0)*1e6/3:.1f} us each (host side)")
+    del pipe

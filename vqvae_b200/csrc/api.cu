@@ -300,12 +300,24 @@ extern "C" int vqb_residual_stack_f32(const float *r, const float *w1_packed, co
 extern "C" int vqb_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream) {
     if (!dst || !src) return VQB_ERR_BAD_ARG;
     if (bytes == 0) return 0;
-    cudaMemcpyKind k;
-    switch (kind) {
-        case 1: k = cudaMemcpyHostToDevice; break;
-        case 2: k = cudaMemcpyDeviceToHost; break;
-        case 3: k = cudaMemcpyDeviceToDevice; break;
-        default: return VQB_ERR_BAD_ARG;
+    if (kind < 1 || kind > 3) return VQB_ERR_BAD_ARG;
+    // Driver entry point (unified addressing: the driver knows which side is pinned host memory).  The copy must
+    // not go through THIS library's statically linked runtime: host buffers pinned by another runtime instance
+    // (torch's) were copied at pageable speed, synchronously, through cudaMemcpyAsync (measured: 8 GB/s).
+    typedef int (*PFN_cuMemcpyAsync)(unsigned long long, unsigned long long, size_t, void *);
+    static PFN_cuMemcpyAsync fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemcpyAsync", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<PFN_cuMemcpyAsync>(p);
+    }();
+    static const bool use_rt = [] { const char *e = getenv("VQB_MEMCPY_RUNTIME"); return e && e[0] == '1'; }();
+    if (fn && !use_rt) {
+        const int rc = fn((unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, bytes, stream);
+        return rc == 0 ? 0 : VQB_ERR_BAD_ARG;
     }
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     return vqb_cuda_status(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
 }

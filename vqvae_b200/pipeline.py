@@ -89,7 +89,7 @@ class _Slot:
 class HostPipeline:
     """``depth`` host batches in flight through ``model`` (a vqvae_b200 ``VQVAE`` on a CUDA device)."""
 
-    def __init__(self, model, batch_shape, depth: int = 3, use_graph: bool = True):
+    def __init__(self, model, batch_shape, depth: int = 3, use_graph: bool = True, raw_copies: bool = True):
         p = next(model.parameters())
         if p.device.type != "cuda":
             raise RuntimeError("HostPipeline needs the model on a CUDA device (there is no CPU path)")
@@ -109,6 +109,7 @@ class HostPipeline:
         self._inflight: Deque[_Slot] = deque()
         self._count = 0
         self._lib = lib()
+        self._raw = bool(raw_copies)
 
     # -- internals ---------------------------------------------------------------------------
     def _finish(self, slot: _Slot) -> HostResult:
@@ -130,7 +131,7 @@ class HostPipeline:
         slot.busy, slot.index = True, self._count
         self._count += 1
         nbytes = self.h2d_bytes
-        if slot.graph is not None and slot.x_hat_ptr is not None and slot.scalars_ptr is not None:
+        if self._raw and slot.graph is not None and slot.x_hat_ptr is not None and slot.scalars_ptr is not None:
             # graph mode: every address is fixed, so the step is a dozen cheap calls (event waits/records, three
             # stream-ordered copies through the C ABI, one graph launch) -- no stream contexts, no Tensor.copy_
             L = self._lib
