@@ -11,6 +11,31 @@ vqvae_b200.set_precision("tf32")
 m = m.cuda().eval()
 B = 256
 hosts = [torch.from_numpy(weights.make_images(B, 32, seed=1 + i)).pin_memory() for i in range(3)]
+import subprocess, tempfile
+QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+SAMPLERS = {"none": None,
+            "smi20": ["nvidia-smi", "-i", "0", f"--query-gpu={QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
+            "smi100": ["nvidia-smi", "-i", "0", f"--query-gpu={QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+            "nvml20": [sys.executable, "tools/clock_sampler.py", "0", "20"]}
+if len(sys.argv) > 1 and sys.argv[1] == "samplers":
+    pipe = vqvae_b200.HostPipeline(m, (B, 3, 32, 32), depth=3)
+    acc = [0.0]
+    def consume(r): acc[0] += float(r.loss)
+    pipe.run((hosts[i % 3] for i in range(12)), consume)
+    for name, cmd in SAMPLERS.items():
+        f = tempfile.NamedTemporaryFile("w+", suffix=".csv")
+        pr = subprocess.Popen(cmd, stdout=f, stderr=subprocess.DEVNULL) if cmd else None
+        time.sleep(0.5)
+        res = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            pipe.run((hosts[i % 3] for i in range(300)), consume)
+            res.append((time.perf_counter() - t0) / 300 * 1e3)
+        if pr: pr.terminate(); pr.wait()
+        f.flush(); nl = len(open(f.name).read().splitlines())
+        print(f"sampler {name}: ms/step {[round(x, 4) for x in res]}  ({nl} sample lines)")
+    sys.exit(0)
 for raw in (False, True):
     pipe = vqvae_b200.HostPipeline(m, (B, 3, 32, 32), depth=3, raw_copies=raw)
     acc = [0.0]
