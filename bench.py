@@ -141,6 +141,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        if gpu_index < 0:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}",
                                        "--format=csv,noheader,nounits", "-lms", "20"],
@@ -277,7 +279,7 @@ def main():
         barrier()
 
         # ---- device-resident timing: K steps, L2 flushed between, events per step ---------
-        clocks = ClockSampler(local_rank)
+        clocks = ClockSampler(local_rank if not os.environ.get('VQB_BENCH_NOSAMPLER') else -1)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         for s0, s1 in evs:
