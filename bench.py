@@ -134,21 +134,38 @@ def run_reference_arm(args, wl, rank, world):
 
 # --------------------------------------------------------------------------- GPU arm
 class ClockSampler:
+    """SM clock / throttle-reason samples every 20 ms from a separate light NVML process (tools/clock_sampler.py;
+    `nvidia-smi --query-gpu -lms 20` as the fallback: its full query cost the pipelined host loop ~8 %)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p, self.kind = None, None
         if gpu_index < 0:
             return
+        # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            phys = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        except (ValueError, IndexError):
+            phys = gpu_index
+        sampler = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "clock_sampler.py")
+        try:
+            import pynvml  # noqa: F401  (only to know the light sampler can run)
+            self.p = subprocess.Popen([sys.executable, sampler, str(phys), "20"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+            self.kind = "nvml"
+        except Exception:
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(phys), f"--query-gpu={self.QUERY}",
+                                           "--format=csv,noheader,nounits", "-lms", "20"],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+                self.kind = "smi"
+            except OSError:
+                self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -160,23 +177,28 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        lines = [r.strip() for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            if len(r) < 9:
-                continue
+        for ln in lines:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                if self.kind == "nvml":                     # "sm,max,reason|reason"
+                    a, b, c = ln.split(",", 2)
+                    sm.append(float(a)); mx.append(float(b))
+                    reasons.update(x for x in c.split("|") if x)
+                else:
+                    r = ln.split(", ")
+                    if len(r) < 9:
+                        continue
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                    for n, v in zip(self.NAMES, r[5:9]):
+                        if v.strip().lower().startswith("active"):
+                            reasons.add(n)
             except ValueError:
                 continue
-            for n, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(n)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), sampler=self.kind)
         return out
 
 
@@ -311,7 +333,7 @@ def main():
         # (2) the package's streaming front end (vqvae_b200.HostPipeline): the same per-step copies and
         # the same forward, `depth` batches in flight so PCIe and kernels overlap (throughput view; this
         # is the e2e number of the JSON line)
-        depth = 3
+        depth = int(os.environ.get('VQB_BENCH_DEPTH', '3'))
         pipe = vqvae_b200.HostPipeline(model, (B, 3, S, S), depth=depth, use_graph=use_graph)
         hosts = [x_host] + [torch.from_numpy(make_images(B, S, seed=101 + i + 7 * rank)).pin_memory()
                             for i in range(depth - 1)]
@@ -379,7 +401,7 @@ def main():
         return dict(value=value, ms_per_step=dev_ms / args.steps, e2e_value=e2e_value, e2e_ms=e2e_s / args.steps * 1e3,
                     launches=int(launches_per_step * args.steps), graph=graph is not None, clocks=clock_info,
                     roofline=roofline, kernels=kernels[:8], h2d=int(h2d_pipe), d2h=int(d2h_pipe),
-                    e2e_sync_value=imgs / e2e_sync_s, e2e_sync_ms=e2e_sync_s / args.steps * 1e3)
+                    e2e_sync_value=imgs / e2e_sync_s, e2e_sync_ms=e2e_sync_s / args.steps * 1e3, depth=depth)
 
     main_mode = run_mode(args.precision)
     extra = {}
@@ -429,8 +451,9 @@ def main():
                    "weights": "synthetic seeded (oracle/weights.py), reference architecture h=128 res_h=32 n_res=2"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": main_mode["h2d"],
                 "d2h_bytes_per_step": main_mode["d2h"], "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "vqvae_b200.HostPipeline(depth=3): every step copies its pinned host batch to HBM, runs the "
-                       "forward and copies x_hat + loss + perplexity back to pinned host memory, 3 steps in flight",
+                "api": f"vqvae_b200.HostPipeline(depth={main_mode['depth']}): every step copies its pinned host batch to "
+                       f"HBM, runs the forward and copies x_hat + loss + perplexity back to pinned host memory, "
+                       f"{main_mode['depth']} steps in flight",
                 "sync_value": main_mode["e2e_sync_value"], "sync_ms_per_step": main_mode["e2e_sync_ms"],
                 "sync_note": "same copies with the caller waiting for each step before submitting the next"},
         "gpu_launches": int(launches_per_step * args.steps),
