@@ -24,16 +24,16 @@ constexpr int CH_MAX_STAGES = 32;     // weight-tile ring: as deep as shared mem
 constexpr int CH_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int CH_HALO_BUFS = 2;       // halo tiles are double buffered: chunk c+2 loads while c+1 computes
 constexpr int CH_MAX_CHUNKS = 8;       // Cin <= 256
-constexpr int WP_DEFAULT = 10;               // halo tile width: 8 pixels + 1 each side.  Not a multiple of 8 on purpose: the swizzle
-                                     // phase of a row comes from its absolute address, for TMA and UMMA alike, so an
-                                     // 8-row operand group may start at any row (SBO = WP rows); 16 wasted 37 % of the tile
+// Halo tile width (p.WP): 8 pixels + 1 each side = 10.  Not a multiple of 8 on purpose: the swizzle phase of a row
+// comes from its absolute address, for TMA and UMMA alike, so an 8-row operand group may start at any row
+// (SBO = WP rows); padding to 16 wasted 37 % of the tile.  VQB_HALO_WP=16 restores the padded layout.
 
 struct ConvHaloParams {
     const float *bias, *skip;
     float *out;
     int B, H, W, Cin, Cout;
     int BH, BN, tiles_x, tiles_y;
-    int stages, relu, bo_mode;
+    int stages, relu;
     int nmma;               // MMA issuer warps (1 or 2): k-step i goes to issuer i % nmma, private accumulators summed
                             // by the epilogue in a fixed order (see res_tc.cu)
     int WP;                 // halo tile width in pixels (10, or 16 with VQB_HALO_WP=16)
@@ -313,7 +313,6 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     q.tiles_x = (p.W + 7) / 8;
     q.tiles_y = (p.H + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
-    q.bo_mode = 0;
     {
         static const int want = [] { const char *e = getenv("VQB_CONV_NMMA"); return (e && atoi(e) == 1) ? 1 : 2; }();
         q.nmma = (want == 2 && 2 * p.Cout <= 256) ? 2 : 1;       // <= 256 TMEM columns: two CTAs per SM can still allocate

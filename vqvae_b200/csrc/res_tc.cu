@@ -34,7 +34,6 @@ extern "C" int vqb_debug_read_trace(unsigned long long *dst, int n) {
 namespace {
 
 constexpr int RT_THREADS = 320;       // warps 0-3 epilogue, 4 TMA producer, 5 TMEM allocator, 6-9 MMA issuers
-constexpr int RT_MAX_ISSUERS = 4;
 constexpr int RT_MAX_STAGES = 32;     // W1 tile ring, as deep as shared memory allows
 constexpr int RT_GROUP = 4;           // ring stages released per tcgen05.commit (a commit costs ~230 cycles)
 constexpr int RT_HALO_BUFS = 2;       // double-buffered halo tiles
@@ -49,6 +48,8 @@ struct ResTcParams {
     int stages;
     int WP;                 // halo tile width in pixels: 8 + 1 each side = 10 (see conv_halo.cu), or 16 (VQB_HALO_WP)
     int relu_out;
+    int nprod;              // W1 producer warps (2 in staged mode: warp 5 takes the odd k-steps; one warp issuing a 4 KB
+                            // box per k-step behind an mbarrier wait could not keep four MMA issuers fed)
     int nmma;               // GEMM1 issuer warps (1, 2 or 4): k-step i goes to issuer i % nmma, each accumulates its own
                             // D1 partial in TMEM; epilogue 1 sums them in a fixed order (deterministic)
     int napp;               // applications of the (shared-weight) layer chained inside the kernel (residual.py:45-50);
@@ -56,7 +57,6 @@ struct ResTcParams {
                             // in the halo buffers (borders = the conv's zero padding) and is rewritten in place
     int staged;             // 1: all halo chunks resident (skip read from smem) and the output tile is
                             //    staged in smem (ring + A2 + W2 region) and TMA-stored
-    int flags;              // perf experiments (env VQB_RES_FLAGS): 1 = skip GEMM1 MMAs, 2 = skip W1 loads/waits
 };
 
 __global__ void __launch_bounds__(RT_THREADS)
@@ -112,7 +112,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::mbar_init(d1full, (uint32_t)p.nmma);           // one commit per issuer
         ptx::mbar_init(a2ready, 4);                         // one arrival per epilogue warp
         ptx::mbar_init(d2full, 1);
-        ptx::mbar_init(actready, 4);                        // one arrival per epilogue warp
+        ptx::mbar_init(actready, p.staged ? 8u : 4u);       // one arrival per epilogue warp (+ the four helper warps)
     }
     if (tid == 128) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w1); }
     if (tid == 160) { ptx::prefetch_tmap(&tma_w2); ptx::prefetch_tmap(&tma_out); }
@@ -126,12 +126,62 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
     if (tid == 128) trace_mark(1);                     // barriers + TMEM ready
 
 
+    // ---- epilogue 2 of the staged layout, columns [c_beg, c_end) of this thread's row: D2 + skip (centre tap of
+    // the resident halo tile) -> ReLU -> either back into the halo buffers in place (chained application: same
+    // thread, same address; pixels outside the image stay zero = the conv's padding) or into the output tile
+    // staged over the dead W1 ring + A2 + W2 (MMA row order, TMA-stored).  Run by the epilogue warps for the
+    // first half of the columns and by warps 6-9 (idle issuers) for the second: one warp per scheduler cannot
+    // hide its own tcgen05.ld / LDS latencies.
+    auto epilogue2_staged = [&](int c_beg, int c_end, bool last) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                      // row = (y * BN + bn) * 8 + x
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int bw = row & 7, grp = row >> 3;
+        const int bn = grp % p.BN, bh = grp / p.BN;
+        const bool valid = gx0 + bw < p.W && gy0 + bh < p.H && n0 + bn < p.B;
+        const int hrow = ((bh + 1) * p.BN + bn) * RT_WP + bw + 1;      // this pixel's row of a halo buffer
+        auto emit = [&](const float (&v)[32], int c0) {
+            unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
+            unsigned char *orow = sm + ring_off + (c0 >> 5) * RT_A_BYTES + row * 128;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+                float4 *ptr = reinterpret_cast<float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
+                const float4 sk = *ptr;
+                float4 o = make_float4(v[c16 * 4] + sk.x, v[c16 * 4 + 1] + sk.y, v[c16 * 4 + 2] + sk.z, v[c16 * 4 + 3] + sk.w);
+                if (p.relu_out) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (last) {
+                    *reinterpret_cast<float4 *>(orow + ((c16 ^ (row & 7)) << 4)) = o;
+                } else {
+                    if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *ptr = o;
+                }
+            }
+        };
+        if (c_beg >= c_end) return;
+        float va[32], vb[32];                               // two TMEM loads in flight
+        ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)c_beg, va);
+        for (int c0 = c_beg; c0 < c_end; c0 += 64) {
+            ptx::tmem_ld_wait32(va);
+            if (c0 + 32 < c_end) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 32), vb);
+            emit(va, c0);
+            if (c0 + 32 < c_end) {
+                ptx::tmem_ld_wait32(vb);
+                if (c0 + 64 < c_end) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 64), va);
+                emit(vb, c0 + 32);
+            }
+        }
+    };
+    const int c_split = ((p.C / 32 + 1) / 2) * 32;          // epilogue warps: [0, c_split), helper warps: [c_split, C)
+
     // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 TMEM allocator, 6.. MMA
     // issuers.  GEMM1 has N = Cmid = 32: the tensor pipe needs ~22 cycles per MMA, one issuing warp manages
     // one per ~135 (barrier wait + descriptor arithmetic per k-step are dependent scalar code), so the k-steps
     // are dealt round-robin to up to four issuer warps with private accumulators.
-    if (warp == 4) {
+    if (warp == 4 || (warp == 5 && p.nprod == 2)) {
         {
+            const int pi = warp - 4, np = p.nprod;
             const bool leader = ptx::elect_one();       // converged warp, one issuing lane
             auto load_halo = [&](int c) {               // input tile + halo of one 32-channel chunk
                 const int b = c % hbufs;
@@ -143,7 +193,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             };
             // weights do not depend on the previous layer: W2 and the first ring-full of W1 tiles are
             // requested BEFORE pdl_wait(), i.e. while the previous kernel is still draining
-            if (leader) {
+            if (leader && pi == 0) {
                 ptx::mbar_expect_tx(w2full, (uint32_t)(matoms * p.C * 128));      // W2 (all of it) once
                 for (int a = 0; a < matoms; ++a)
                     ptx::tma_load_2d(sbase + w2_off + a * p.C * 128, &tma_w2, w2full, a * 32, 0);
@@ -151,12 +201,29 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             const int ksteps = 9 * chunks * p.napp;     // the same W1 tiles stream once per application
             const int prefill = S < ksteps ? S : ksteps;
             if (leader)
-                for (int i = 0; i < prefill; ++i) {
+                for (int i = pi; i < prefill; i += np) {
                     ptx::mbar_expect_tx(bars + 8u * i, (uint32_t)stage_bytes);
                     ptx::tma_load_2d(sbase + ring_off + i * stage_bytes, &tma_w1, bars + 8u * i, ((i / 9) % chunks) * 32, (i % 9) * p.Cmid);
                 }
-            pdl_wait();                                 // the input activation is the previous layer's output
-            for (int c = 0; c < hbufs; ++c) load_halo(c);
+            if (pi == 0) {
+                pdl_wait();                             // the input activation is the previous layer's output
+                for (int c = 0; c < hbufs; ++c) load_halo(c);
+            }
+            if (np == 2) {
+                // staged mode (no halo reloads): this producer streams the k-steps >= prefill of its parity
+                int kidx = prefill + ((pi - prefill) & 1);
+                uint32_t st = (uint32_t)(kidx % S), pass = (uint32_t)(kidx / S);
+                int t = kidx % 9, c = (kidx / 9) % chunks;
+                for (; kidx < ksteps; kidx += 2) {
+                    ptx::mbar_wait(empty((int)(st / RT_GROUP)), (pass - 1u) & 1u);      // the group's previous use is released
+                    if (leader) {
+                        ptx::mbar_expect_tx(full((int)st), (uint32_t)stage_bytes);
+                        ptx::tma_load_2d(sbase + ring_off + st * (uint32_t)stage_bytes, &tma_w1, full((int)st), c * 32, t * p.Cmid);
+                    }
+                    st += 2; if (st >= (uint32_t)S) { st -= (uint32_t)S; ++pass; }
+                    t += 2; if (t >= 9) { t -= 9; if (++c == chunks) c = 0; }
+                }
+            } else {
             // W1 tiles stream through the ring; running pointers, no div/mod in the loop
             uint32_t st = 0, par = 0, full_bar = bars, empty_bar = bars + 8u * RT_MAX_STAGES;
             uint32_t dst = sbase + ring_off;
@@ -180,10 +247,12 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     }
                 }
             }
+            }
         }
-    } else if (warp >= 6 && warp - 6 < p.nmma) {
+    } else if (warp >= 6) {
         {
             const int mi = warp - 6, nm = p.nmma;
+            const bool issuer = mi < nm;
             const bool leader = ptx::elect_one();       // all 32 lanes run the loop; only `leader` issues
             const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.Cmid);
             const uint32_t idesc2 = ptx::instr_desc(ptx::FMT_TF32, 128, (uint32_t)p.C);
@@ -202,7 +271,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     ptx::mbar_wait(actready, ap ^ 1u);
                     ptx::tc_fence_after();
                 }
-                for (int c = 0; c < chunks; ++c, kbase += 9) {
+                for (int c = 0; issuer && c < chunks; ++c, kbase += 9) {
                     const int hb = c % hbufs;
                     ptx::mbar_wait(hfull(hb), (uint32_t)((c / hbufs) & 1));
                     if (leader && app == 0 && mi == 0) { if (c == 0) trace_mark(2); else trace_mark(2 + c); }
@@ -230,7 +299,7 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     if (leader && !p.staged) ptx::tc_commit(hempty(hb));     // chunk done: its halo buffer may be refilled
                     __syncwarp();
                 }
-                if (leader) { ptx::tc_commit(d1full); if (app == 0 && mi == 0) trace_mark(8); }    // this issuer's GEMM1 MMAs issued
+                if (leader && issuer) { ptx::tc_commit(d1full); if (app == 0 && mi == 0) trace_mark(8); }    // this issuer's GEMM1 MMAs issued
                 if (mi == 0) {
                     // GEMM2 once the epilogue has written relu(D1) as the A2 operand
                     if (app == 0) ptx::mbar_wait(w2full, 0);
@@ -246,6 +315,21 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
                     if (leader) { ptx::tc_commit(d2full); if (app == 0) trace_mark(11); }   // GEMM2 issued
                 }
                 __syncwarp();
+                if (p.staged) {
+                    // second half of epilogue 2 (this warp's TMEM lane quadrant is warp % 4)
+                    const bool last = app + 1 == p.napp;
+                    ptx::mbar_wait_sleep(d2full, ap, 64);
+                    ptx::tc_fence_after();
+                    epilogue2_staged(c_split, p.C, last);
+                    ptx::fence_proxy_async();
+                    if (last) {
+                        ptx::named_bar_sync(1, 256);             // with the four epilogue warps; tid 0 then stores the tile
+                    } else {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(actready);
+                    }
+                }
             }
         }
     } else if (warp < 4) {
@@ -307,36 +391,8 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
         ptx::tc_fence_after();
         if (tid == 0 && app < 2) trace_mark(12 + 16 * app);      // GEMM2 complete
         if (!last) {
-            // chained application (staged mode, whole images per tile): r_{a+1} = act(r_a + D2) replaces r_a in
-            // the halo buffers, same thread, same address; pixels outside the image stay zero (= conv padding)
-            auto rewrite = [&](const float (&v)[32], int c0) {
-                unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
-#pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
-                    float4 *ptr = reinterpret_cast<float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
-                    const float4 sk = *ptr;
-                    float4 o = make_float4(v[c16 * 4] + sk.x, v[c16 * 4 + 1] + sk.y, v[c16 * 4 + 2] + sk.z, v[c16 * 4 + 3] + sk.w);
-                    if (p.relu_out) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *ptr = o;
-                }
-            };
-            // two TMEM loads in flight: the next 32 columns travel while these are added and written
-            // (a tcgen05.ld round trip is ~0.2 us; four in sequence were half of this phase)
-            float va[32], vb[32];
-            ptx::tmem_ld32(lane_taddr + d2col, va);
-            for (int c0 = 0; c0 < p.C; c0 += 64) {
-                ptx::tmem_ld_wait32(va);
-                if (c0 + 32 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 32), vb);
-                rewrite(va, c0);
-                if (c0 + 32 < p.C) {
-                    ptx::tmem_ld_wait32(vb);
-                    if (c0 + 64 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 64), va);
-                    rewrite(vb, c0 + 32);
-                }
-            }
+            // chained application (staged mode, whole images per tile): r_{a+1} = act(r_a + D2) replaces r_a
+            epilogue2_staged(0, c_split, false);
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
             __syncwarp();
@@ -345,36 +401,9 @@ res_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant_
             continue;
         }
         if (p.staged) {
-            // skip = centre tap of the resident halo tiles; output tile staged in shared memory (over the
-            // W1 ring + A2 + W2, all dead once GEMM2 has completed) in MMA row order and TMA-stored:
-            // no global skip loads, no scattered 16-byte stores.
-            auto stage = [&](const float (&v)[32], int c0) {
-                const unsigned char *srow = sm + (c0 >> 5) * halo_stride + hrow * 128;
-                unsigned char *orow = sm + ring_off + (c0 >> 5) * RT_A_BYTES + row * 128;
-#pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
-                    const float4 sk = *reinterpret_cast<const float4 *>(srow + ((c16 ^ (hrow & 7)) << 4));
-                    float4 o = make_float4(v[c16 * 4] + sk.x, v[c16 * 4 + 1] + sk.y, v[c16 * 4 + 2] + sk.z, v[c16 * 4 + 3] + sk.w);
-                    if (p.relu_out) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4 *>(orow + ((c16 ^ (row & 7)) << 4)) = o;
-                }
-            };
-            float va[32], vb[32];
-            ptx::tmem_ld32(lane_taddr + d2col, va);
-            for (int c0 = 0; c0 < p.C; c0 += 64) {
-                ptx::tmem_ld_wait32(va);
-                if (c0 + 32 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 32), vb);
-                stage(va, c0);
-                if (c0 + 32 < p.C) {
-                    ptx::tmem_ld_wait32(vb);
-                    if (c0 + 64 < p.C) ptx::tmem_ld32(lane_taddr + d2col + (uint32_t)(c0 + 64), va);
-                    stage(vb, c0 + 32);
-                }
-            }
+            epilogue2_staged(0, c_split, true);
             ptx::fence_proxy_async();
-            ptx::named_bar_sync(1, 128);                       // the four epilogue warps
+            ptx::named_bar_sync(1, 256);                       // the four epilogue warps + the four helper warps
             if (tid == 0) {
                 for (int a = 0; a < p.C / 32; ++a)               // box {32 ch, 8 px, BN img, BH rows}; OOB rows are clipped
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
@@ -431,10 +460,6 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     if (!res_tc_supported(C, Cmid, r, out) || napp < 1) return VQB_ERR_UNSUPPORTED;
     if (napp > 1 && !relu_out) return VQB_ERR_UNSUPPORTED;      // a chained layer input must be relu(x)
     ResTcParams q;
-    {
-        const char *fl = getenv("VQB_RES_FLAGS");
-        q.flags = fl ? atoi(fl) : 0;
-    }
     q.napp = napp;
     {
         static const int want = [] { const char *e = getenv("VQB_RES_NMMA"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
@@ -509,6 +534,10 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
         if (stages < RT_GROUP) return VQB_ERR_UNSUPPORTED;
     }
     q.stages = stages;
+    {
+        static const int want = [] { const char *e = getenv("VQB_RES_NPROD"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        q.nprod = (q.staged && stages % 2 == 0) ? want : 1;
+    }
     const int smem = stages * stage_bytes + fixed;
     static int attr_max = 0;
     if (smem > attr_max) {
