@@ -18,6 +18,39 @@ SAMPLERS = {"none": None,
             "smi20": ["nvidia-smi", "-i", "0", f"--query-gpu={QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
             "smi100": ["nvidia-smi", "-i", "0", f"--query-gpu={QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
             "nvml20": [sys.executable, "tools/clock_sampler.py", "0", "20"]}
+if len(sys.argv) > 1 and sys.argv[1] == "benchlike":
+    # what does bench.py do before its pipelined e2e region that a bare loop does not?
+    what = sys.argv[2] if len(sys.argv) > 2 else "all"
+    x_dev = hosts[0].cuda()
+    if what in ("flush", "all"):
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        for _ in range(20): flush.zero_()
+    if what in ("graph", "all"):
+        static_x = x_dev.clone()
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2): m(static_x)
+        torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g): out = m(static_x)
+        for _ in range(30): g.replay()
+        torch.cuda.synchronize()
+    if what in ("events", "all"):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+        for a, b in evs: a.record(); b.record()
+        torch.cuda.synchronize()
+    pipe = vqvae_b200.HostPipeline(m, (B, 3, 32, 32), depth=3)
+    acc = [0.0]
+    def consume(r): acc[0] += float(r.loss)
+    pipe.run((hosts[i % 3] for i in range(6)), consume)
+    torch.cuda.synchronize()
+    res = []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        pipe.run((hosts[i % 3] for i in range(200)), consume)
+        res.append((time.perf_counter() - t0) / 200 * 1e3)
+    print(f"benchlike {what}: ms/step {[round(x, 4) for x in res]}")
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "samplers":
     pipe = vqvae_b200.HostPipeline(m, (B, 3, 32, 32), depth=3)
     acc = [0.0]
