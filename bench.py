@@ -321,7 +321,7 @@ def main():
             xh_host.copy_(o[1], non_blocking=True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(0 if os.environ.get('VQB_BENCH_NOSYNC') else args.steps):
+        for _ in range(args.steps):
             static_x.copy_(x_host, non_blocking=True)
             o = step()
             xh_host.copy_(o[1], non_blocking=True)
@@ -344,12 +344,18 @@ def main():
             seen[1] += float(r.loss)                      # the caller reads each step's result on the host
 
         pipe.run((hosts[i % depth] for i in range(2 * depth)), consume)   # warm
-        barrier()
-        seen[0] = 0
-        t0 = time.perf_counter()
-        pipe.run((hosts[i % depth] for i in range(args.steps)), consume)
-        e2e_s = time.perf_counter() - t0
-        assert seen[0] == args.steps and np.isfinite(seen[1])
+        # three regions of exactly K steps each, the median is reported (all three are in the JSON line): the
+        # host loop of a 0.15 ms step is sensitive to scheduling noise on a shared box (0.166-0.31 ms observed
+        # for identical runs), which says nothing about the code under test
+        regions = []
+        for _ in range(3):
+            barrier()
+            seen[0] = 0
+            t0 = time.perf_counter()
+            pipe.run((hosts[i % depth] for i in range(args.steps)), consume)
+            regions.append(time.perf_counter() - t0)
+            assert seen[0] == args.steps and np.isfinite(seen[1])
+        e2e_s = sorted(regions)[1]
         h2d_pipe, d2h_pipe = pipe.h2d_bytes, pipe.d2h_bytes
         del pipe
         barrier()
@@ -401,7 +407,8 @@ def main():
         return dict(value=value, ms_per_step=dev_ms / args.steps, e2e_value=e2e_value, e2e_ms=e2e_s / args.steps * 1e3,
                     launches=int(launches_per_step * args.steps), graph=graph is not None, clocks=clock_info,
                     roofline=roofline, kernels=kernels[:8], h2d=int(h2d_pipe), d2h=int(d2h_pipe),
-                    e2e_sync_value=imgs / e2e_sync_s, e2e_sync_ms=e2e_sync_s / args.steps * 1e3, depth=depth)
+                    e2e_sync_value=imgs / e2e_sync_s, e2e_sync_ms=e2e_sync_s / args.steps * 1e3, depth=depth,
+                    e2e_regions_ms=[r / args.steps * 1e3 for r in regions])
 
     main_mode = run_mode(args.precision)
     extra = {}
@@ -454,6 +461,8 @@ def main():
                 "api": f"vqvae_b200.HostPipeline(depth={main_mode['depth']}): every step copies its pinned host batch to "
                        f"HBM, runs the forward and copies x_hat + loss + perplexity back to pinned host memory, "
                        f"{main_mode['depth']} steps in flight",
+                "regions_ms_per_step": main_mode["e2e_regions_ms"],
+                "regions_note": "three timed regions of K steps each; value = the median region (max over ranks)",
                 "sync_value": main_mode["e2e_sync_value"], "sync_ms_per_step": main_mode["e2e_sync_ms"],
                 "sync_note": "same copies with the caller waiting for each step before submitting the next"},
         "gpu_launches": int(launches_per_step * args.steps),
