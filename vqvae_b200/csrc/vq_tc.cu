@@ -372,6 +372,19 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
                 const int gbase = (c * CN + h * 128) / 8;
                 float va[32], vb[32], warm[8];
+                // A full list is first compacted against the CURRENT threshold (entries pushed while the running
+                // minimum was still high are dropped: the final threshold can only be lower), and only a list that
+                // is still full afterwards sends the row to the exact scan of every code.  Without this, about one
+                // row in 10^5 overflowed on ordinary data, and that single row cost the whole kernel 50 us
+                // (19 -> 70 us for one of three cfg2 batches, profiles/r01_step_launch_list_tf32.txt).
+                auto compact = [&]() {
+                    int m = 0;
+                    for (int sidx = 0; sidx < LCAP - 1; ++sidx) {
+                        const float2 ent = lists[sidx * 256 + et];
+                        if (ent.x <= thr) { lists[m * 256 + et] = ent; ++m; }
+                    }
+                    cnt = m;
+                };
                 auto process = [&](const float (&v)[32], int j) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -400,9 +413,11 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         } else {
                             // branch-free push: always write slot min(cnt, LCAP-1), keep it when in range
                             lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
-                            cnt += (gm <= thr) ? 1 : 0;
+                            const bool pushed = gm <= thr;
+                            cnt += pushed ? 1 : 0;
                             run_min = fminf(run_min, gm);
                             thr = run_min + tau;
+                            if (pushed && cnt == LCAP - 1) compact();
                         }
                     }
                     if (c == 0 && j == 1) {
@@ -411,7 +426,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         for (int i = 0; i < 8; ++i) {
                             lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(warm[i], __int_as_float(gbase + i));
                             cnt += (warm[i] <= thr) ? 1 : 0;
-                        }
+                        }                                   // (at most 8 entries: cannot fill the list)
                     }
                 };
                 if (!(p.flags & 2)) {
