@@ -63,7 +63,6 @@ constexpr int CN = 256;          // codes per chunk (UMMA N)
 constexpr int DD = 64;           // embedding dim handled by this kernel
 constexpr int NTHREADS = 384;    // 12 warps
 constexpr int LCAP = 12;         // group list capacity per thread (pass 1)
-constexpr int CMAX = 4;          // candidate groups per thread after filtering
 constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
 constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
 constexpr int HIST_MAX = 1024;
@@ -72,7 +71,7 @@ constexpr int OFF_Z = 0;
 constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;
 constexpr int OFF_LIST = OFF_B + 2 * CN * 4;
-constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;      // float[256]; reused as int nc[256]
+constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;      // (1 KB spare)
 constexpr int OFF_XBD = OFF_XMIN + 256 * 4;              // float[256]
 constexpr int OFF_XBK = OFF_XBD + 256 * 4;               // int[256]
 constexpr int OFF_HIST = OFF_XBK + 256 * 4;
@@ -318,8 +317,6 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
         }
         float2 *lists = reinterpret_cast<float2 *>(sm + OFF_LIST);
-        float *xmin = reinterpret_cast<float *>(sm + OFF_XMIN);
-        int *xnc = reinterpret_cast<int *>(sm + OFF_XMIN);
         float *xbd = reinterpret_cast<float *>(sm + OFF_XBD);
         int *xbk = reinterpret_cast<int *>(sm + OFF_XBK);
         const int Kpad = nchunks * CN;
@@ -372,19 +369,6 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
                 const int gbase = (c * CN + h * 128) / 8;
                 float va[32], vb[32], warm[8];
-                // A full list is first compacted against the CURRENT threshold (entries pushed while the running
-                // minimum was still high are dropped: the final threshold can only be lower), and only a list that
-                // is still full afterwards sends the row to the exact scan of every code.  Without this, about one
-                // row in 10^5 overflowed on ordinary data, and that single row cost the whole kernel 50 us
-                // (19 -> 70 us for one of three cfg2 batches, profiles/r01_step_launch_list_tf32.txt).
-                auto compact = [&]() {
-                    int m = 0;
-                    for (int sidx = 0; sidx < LCAP - 1; ++sidx) {
-                        const float2 ent = lists[sidx * 256 + et];
-                        if (ent.x <= thr) { lists[m * 256 + et] = ent; ++m; }
-                    }
-                    cnt = m;
-                };
                 auto process = [&](const float (&v)[32], int j) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -413,11 +397,9 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         } else {
                             // branch-free push: always write slot min(cnt, LCAP-1), keep it when in range
                             lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(gm, __int_as_float(gbase + j * 4 + g));
-                            const bool pushed = gm <= thr;
-                            cnt += pushed ? 1 : 0;
+                            cnt += (gm <= thr) ? 1 : 0;
                             run_min = fminf(run_min, gm);
                             thr = run_min + tau;
-                            if (pushed && cnt == LCAP - 1) compact();
                         }
                     }
                     if (c == 0 && j == 1) {
@@ -426,7 +408,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         for (int i = 0; i < 8; ++i) {
                             lists[min(cnt, LCAP - 1) * 256 + et] = make_float2(warm[i], __int_as_float(gbase + i));
                             cnt += (warm[i] <= thr) ? 1 : 0;
-                        }                                   // (at most 8 entries: cannot fill the list)
+                        }
                     }
                 };
                 if (!(p.flags & 2)) {
@@ -452,40 +434,14 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             }
 
             vq_mark(tr, it, 6);
-            // ---- approximate minimum of the whole row (both column halves) ----
-            xmin[et] = run_min;
+            // ---- exchange with the partner thread (same row, other column half): running minimum and list length
+            // travel through the scratch slot of this thread's own list (slot LCAP-1, never a valid entry) ----
+            lists[(LCAP - 1) * 256 + et] = make_float2(run_min, __int_as_float((slow_row || cnt >= LCAP) ? -1 : cnt));
             ptx::named_bar_sync(1 + q, 64);
-            thr = fminf(run_min, xmin[et ^ 128]) + tau;
-
-            // ---- filter the list down to the groups that can hold the canonical winner ----
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nc = 0;
-            if (cnt >= LCAP) slow_row = true;      // slot LCAP-1 is the scratch slot of the branch-free push
-            if (!slow_row) {
-                for (int s = 0; s < cnt; ++s) {
-                    const float2 ent = lists[s * 256 + et];
-                    if (ent.x <= thr) {
-                        const int g = __float_as_int(ent.y);
-                        if (nc == 0) c0 = g; else if (nc == 1) c1 = g; else if (nc == 2) c2 = g; else c3 = g;
-                        ++nc;
-                    }
-                }
-                if (nc > CMAX) slow_row = true;
-            }
-            // candidates travel to the partner through this thread's OWN last two list slots
-            // (no other thread ever touches them), the count through xnc (aliases xmin, hence
-            // the extra barrier: the partner must have read xmin first).
-            ptx::named_bar_sync(1 + q, 64);
-            lists[(LCAP - 2) * 256 + et] = make_float2(__int_as_float(c0), __int_as_float(c1));
-            lists[(LCAP - 1) * 256 + et] = make_float2(__int_as_float(c2), __int_as_float(c3));
-            xnc[et] = slow_row ? -1 : nc;
-            ptx::named_bar_sync(1 + q, 64);
-            const int pnc = xnc[et ^ 128];
-            int4 pc;
-            {
-                const float2 lo = lists[(LCAP - 2) * 256 + (et ^ 128)], hi = lists[(LCAP - 1) * 256 + (et ^ 128)];
-                pc = make_int4(__float_as_int(lo.x), __float_as_int(lo.y), __float_as_int(hi.x), __float_as_int(hi.y));
-            }
-            if (pnc < 0) slow_row = true;
+            const float2 pinfo = lists[(LCAP - 1) * 256 + (et ^ 128)];
+            thr = fminf(run_min, pinfo.x) + tau;            // approximate minimum of the whole row + tau
+            const int pcnt = __float_as_int(pinfo.y);
+            if (cnt >= LCAP || pcnt < 0) slow_row = true;   // a full list (either half) -> exact scan of every code
 
             vq_mark(tr, it, 7);
             // ---- z row -> registers (needed for the exact chains and for z_q) ----
@@ -557,15 +513,22 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 consider(M0, kg + j0); consider(M1, kg + j1); consider(M2, kg + j2); consider(M3, kg + j3);
             };
             if (p.flags & 1) {
-                bk = (nc > 0) ? c0 * 8 : ((pnc > 0) ? pc.x * 8 : 0);    // timing experiment only
+                bk = 0;                                         // timing experiment only
             } else if (!slow_row) {
-                // both threads of the row walk the union of the two lists; each takes 4 of the 8 codes
-                const int total = nc + pnc;
-                for (int t = 0; t < total; ++t) {
-                    int g;
-                    if (t < nc) g = (t == 0) ? c0 : (t == 1) ? c1 : (t == 2) ? c2 : c3;
-                    else { const int u = t - nc; g = (u == 0) ? pc.x : (u == 1) ? pc.y : (u == 2) ? pc.z : pc.w; }
-                    if (g * 8 < p.K) rescore_group(g);
+                // Both threads of the row walk BOTH lists (their own, then the partner's, straight from shared
+                // memory) and re-score every listed group whose minimum is within tau of the row minimum; each
+                // takes 4 of the 8 codes.  No cap on the number of candidate groups: a cap of 4 per half sent about
+                // one row in 10^5 to the exact scan of all K codes, which cost the whole kernel 50 us
+                // (19 -> 70 us for one cfg2 batch in three).
+                for (int sidx = 0; sidx < cnt; ++sidx) {
+                    const float2 ent = lists[sidx * 256 + et];
+                    const int g = __float_as_int(ent.y);
+                    if (ent.x <= thr && g * 8 < p.K) rescore_group(g);
+                }
+                for (int sidx = 0; sidx < pcnt; ++sidx) {
+                    const float2 ent = lists[sidx * 256 + (et ^ 128)];
+                    const int g = __float_as_int(ent.y);
+                    if (ent.x <= thr && g * 8 < p.K) rescore_group(g);
                 }
             } else {
                 // non-finite data or overflowing lists (e.g. many duplicated codes): every code, exactly
