@@ -71,7 +71,7 @@ constexpr int OFF_Z = 0;
 constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;
 constexpr int OFF_LIST = OFF_B + 2 * CN * 4;
-constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;      // (1 KB spare)
+constexpr int OFF_XMIN = OFF_LIST + 256 * LCAP * 8;      // int nc[256]: compacted list lengths
 constexpr int OFF_XBD = OFF_XMIN + 256 * 4;              // float[256]
 constexpr int OFF_XBK = OFF_XBD + 256 * 4;               // int[256]
 constexpr int OFF_HIST = OFF_XBK + 256 * 4;
@@ -317,6 +317,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
         }
         float2 *lists = reinterpret_cast<float2 *>(sm + OFF_LIST);
+        int *xnc = reinterpret_cast<int *>(sm + OFF_XMIN);
         float *xbd = reinterpret_cast<float *>(sm + OFF_XBD);
         int *xbk = reinterpret_cast<int *>(sm + OFF_XBK);
         const int Kpad = nchunks * CN;
@@ -434,14 +435,28 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             }
 
             vq_mark(tr, it, 6);
-            // ---- exchange with the partner thread (same row, other column half): running minimum and list length
-            // travel through the scratch slot of this thread's own list (slot LCAP-1, never a valid entry) ----
-            lists[(LCAP - 1) * 256 + et] = make_float2(run_min, __int_as_float((slow_row || cnt >= LCAP) ? -1 : cnt));
+            // ---- exchange with the partner thread (same row, other column half).  The running minimum travels
+            // through the scratch slot of this thread's own list (slot LCAP-1, never a valid entry). ----
+            lists[(LCAP - 1) * 256 + et] = make_float2(run_min, __int_as_float((slow_row || cnt >= LCAP) ? -1 : 0));
             ptx::named_bar_sync(1 + q, 64);
-            const float2 pinfo = lists[(LCAP - 1) * 256 + (et ^ 128)];
-            thr = fminf(run_min, pinfo.x) + tau;            // approximate minimum of the whole row + tau
-            const int pcnt = __float_as_int(pinfo.y);
-            if (cnt >= LCAP || pcnt < 0) slow_row = true;   // a full list (either half) -> exact scan of every code
+            {
+                const float2 pinfo = lists[(LCAP - 1) * 256 + (et ^ 128)];
+                thr = fminf(run_min, pinfo.x) + tau;        // approximate minimum of the whole row + tau
+                if (cnt >= LCAP || __float_as_int(pinfo.y) < 0) slow_row = true;   // a full list -> exact scan of every code
+            }
+            // ---- compact the list in place down to the groups that can hold the canonical winner; the partner
+            // reads them straight from shared memory (no cap on their number) ----
+            int nc = 0;
+            if (!slow_row) {
+                for (int sidx = 0; sidx < cnt; ++sidx) {
+                    const float2 ent = lists[sidx * 256 + et];
+                    if (ent.x <= thr) { lists[nc * 256 + et] = ent; ++nc; }
+                }
+            }
+            xnc[et] = slow_row ? -1 : nc;
+            ptx::named_bar_sync(1 + q, 64);
+            const int pnc = xnc[et ^ 128];
+            if (pnc < 0) slow_row = true;
 
             vq_mark(tr, it, 7);
             // ---- z row -> registers (needed for the exact chains and for z_q) ----
@@ -515,20 +530,14 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             if (p.flags & 1) {
                 bk = 0;                                         // timing experiment only
             } else if (!slow_row) {
-                // Both threads of the row walk BOTH lists (their own, then the partner's, straight from shared
-                // memory) and re-score every listed group whose minimum is within tau of the row minimum; each
-                // takes 4 of the 8 codes.  No cap on the number of candidate groups: a cap of 4 per half sent about
+                // Both threads of the row walk BOTH compacted lists (their own, then the partner's, straight from
+                // shared memory); each takes 4 of the 8 codes of a group.  No cap on the number of candidate groups: a cap of 4 per half sent about
                 // one row in 10^5 to the exact scan of all K codes, which cost the whole kernel 50 us
                 // (19 -> 70 us for one cfg2 batch in three).
-                for (int sidx = 0; sidx < cnt; ++sidx) {
-                    const float2 ent = lists[sidx * 256 + et];
-                    const int g = __float_as_int(ent.y);
-                    if (ent.x <= thr && g * 8 < p.K) rescore_group(g);
-                }
-                for (int sidx = 0; sidx < pcnt; ++sidx) {
-                    const float2 ent = lists[sidx * 256 + (et ^ 128)];
-                    const int g = __float_as_int(ent.y);
-                    if (ent.x <= thr && g * 8 < p.K) rescore_group(g);
+                const int total = nc + pnc;
+                for (int t = 0; t < total; ++t) {
+                    const int g = __float_as_int(t < nc ? lists[t * 256 + et].y : lists[(t - nc) * 256 + (et ^ 128)].y);
+                    if (g * 8 < p.K) rescore_group(g);
                 }
             } else {
                 // non-finite data or overflowing lists (e.g. many duplicated codes): every code, exactly
