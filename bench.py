@@ -260,6 +260,8 @@ def main():
         """Measure one precision mode; returns the fields of the JSON line that depend on it."""
         vqvae_b200.set_precision(prec)
         # ---- the step: eager once (also packs weights), then captured in a CUDA graph ----
+        model(x_dev)                                  # first call packs the weights (not part of a step)
+        torch.cuda.synchronize()
         l0 = ops.launch_count()
         loss, x_hat, perp = model(x_dev)
         torch.cuda.synchronize()
@@ -478,6 +480,16 @@ def main():
         dist.destroy_process_group()
 
 
+def ncu_traffic(label):
+    """DRAM bytes (read + write) of one launch of the kernel behind `label`, from the committed `ncu --set full`
+    capture of this round (profiles/r01_step_kernels_traffic.json); None when that shape was not captured."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_kernels_traffic.json")) as f:
+            return json.load(f)["kernels"].get(label, {}).get("traffic")
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def kernel_roofline(top, B, S, K, D, peaks, precision):
     """Roofline of the dominant C-ABI call from its label (algorithmic work per launch,
     DESIGN.md 'Kernels and rooflines')."""
@@ -493,10 +505,10 @@ def kernel_roofline(top, B, S, K, D, peaks, precision):
         if t_tc >= t_hbm:
             ach = flops / (ms * 1e-3) / 1e12
             return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"]}
+                    "frac": ach / tensor_peak, "traffic": ncu_traffic(label), "peak_source": peaks["src"]}
         ach = byts / (ms * 1e-3) / 1e9
         return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
+                "frac": ach / peaks["hbm"], "traffic": ncu_traffic(label), "peak_source": peaks["src"]}
     parts = label.split()
     if parts[0] == "res":                       # "res [xN] C->Cmid->C HxW": N x (3x3 C->Cmid then 1x1 Cmid->C)
         napp = 1
@@ -509,7 +521,7 @@ def kernel_roofline(top, B, S, K, D, peaks, precision):
         tensor_peak = peaks["bf16"] * (1.0 if precision == "bf16" else 0.5)
         ach = flops / (ms * 1e-3) / 1e12
         return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"],
+                "frac": ach / tensor_peak, "traffic": ncu_traffic(label), "peak_source": peaks["src"],
                 "note": "tf32/fp32 layers are held against half the measured bf16 cuBLAS peak"}
     # conv label: "conv[T] Cin->Cout k{k}s{s} HxW[ +skip]"
     transposed = parts[0] == "convT"
@@ -526,7 +538,7 @@ def kernel_roofline(top, B, S, K, D, peaks, precision):
     tensor_peak = peaks["bf16"] * (1.0 if precision == "bf16" else 0.5)
     ach = flops / (ms * 1e-3) / 1e12
     return {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": ach / tensor_peak, "traffic": None, "peak_source": peaks["src"],
+            "frac": ach / tensor_peak, "traffic": ncu_traffic(label), "peak_source": peaks["src"],
             "note": "tf32/fp32 layers are held against half the measured bf16 cuBLAS peak"}
 
 
