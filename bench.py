@@ -475,9 +475,40 @@ def main():
         "peaks": peaks,
     }
     line.update(extra)
+    line["vq_kernel"] = vq_kernel_probe(ops, peaks, dev, K, D)      # never raises: a failure is reported in the object
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def vq_kernel_probe(ops, peaks, dev, K, D):
+    """The VQ kernel alone at a streaming size (the 'VQ kernel HBM GB/s' half of BASELINE.json's metric): N = 2^20
+    rows (268 MB in, 268 MB + 8 MB out: larger than L2, so no flush is needed), CUDA events around 10 calls of
+    vqb_vq_forward_f32 (the fused kernel + its 3 us SSE reduction), algorithmic bytes = (2*D*4 + 8) per row."""
+    try:
+        rng = np.random.RandomState(0)
+        N = 1 << 20
+        z = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).to(dev)
+        E = torch.from_numpy(rng.standard_normal((K, D)).astype(np.float32)).to(dev)
+        for _ in range(3):
+            ops.vq_forward(z, E)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            ops.vq_forward(z, E)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        byts = N * (2 * D * 4 + 8)
+        gbs = byts / (ms * 1e-3) / 1e9
+        return {"rows": N, "K": K, "D": D, "ms_per_call": ms, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"],
+                "unit": "GB/s", "frac": gbs / peaks["hbm"], "algorithmic_bytes_per_row": 2 * D * 4 + 8,
+                "tensor_tflops": 2.0 * N * K * D / (ms * 1e-3) / 1e12, "peak_source": peaks["src"],
+                "note": "codebook N(0,1), rows N(0,1); idx/z_q bit-exact vs the canonical fp32 order (tests)"}
+    except Exception as e:  # pragma: no cover - reported, never fatal for the benchmark line
+        return {"error": repr(e)[:200]}
 
 
 def ncu_traffic(label):
