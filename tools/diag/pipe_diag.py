@@ -1,7 +1,7 @@
 """Diagnostic (not a test): which batches of the eager HostPipeline differ from the direct forward."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import vqvae_b200
 from oracle import weights
 

@@ -1,7 +1,7 @@
 """Diagnostic: HostPipeline throughput, torch copies vs raw stream-ordered copies."""
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import vqvae_b200
 from oracle import weights
 sd = weights.make_state_dict(128, 32, 2, 512, 64, seed=5)
