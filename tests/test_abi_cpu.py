@@ -43,6 +43,18 @@ def test_argument_validation_without_a_gpu():
     assert lib.vqb_vq_forward_f32(None, None, 1, 1, 4, None, None, None, None, None, 0, None) == -1
     assert lib.vqb_set_vq_kernel(7) == -1
     assert lib.vqb_vq_workspace_bytes(1024, 512, 64) > 0
+    assert lib.vqb_vq_forward_deferred_f32(None, None, 1, 1, 4, None, None, None, None, None, 0, None) == -1
+    assert lib.vqb_vq_reduce_sse_f32(None, 1, 1, 4, None, None) == -1
+    assert lib.vqb_residual_layer_f32(None, None, None, None, None, 1, 8, 8, 32, 32, 1, 1, None) == -1
+    assert lib.vqb_residual_stack_f32(None, None, None, None, None, None, 1, 8, 8, 32, 32, 2, 1, None) == -1
+    import ctypes
+    buf = (ctypes.c_float * 4)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.vqb_residual_stack_f32(p, p, p, p, p, p, 1, 8, 8, 32, 32, 0, 1, None) == -1      # n_layers < 1
+    assert lib.vqb_residual_stack_f32(p, p, p, p, None, p, 1, 8, 8, 32, 32, 2, 1, None) == -1   # scratch needed for n > 1
+    assert lib.vqb_memcpy_async(None, p, 16, 1, None) == -1
+    assert lib.vqb_memcpy_async(p, p, 16, 9, None) == -1                                        # unknown kind
+    assert lib.vqb_memcpy_async(p, p, 0, 1, None) == 0                                          # empty copy is a no-op
 
 
 def test_reference_constructor_signatures_and_import_paths():
