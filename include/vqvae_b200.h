@@ -10,10 +10,16 @@
  * stub a maintainer of the reference would add.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer owned by the caller (PyTorch in practice);
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch in practice)
+ *     unless stated otherwise;
  *     the library never allocates, frees or retains device memory;
  *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous, make no
  *     host synchronisation and are CUDA-graph capturable;
+ *   - one CUDA device per process (the deployment model is one process per GPU,
+ *     SURVEY.md 8e): the opt-in shared-memory size of each kernel is configured once
+ *     per process, on the device that is current at its first launch; calls may come
+ *     from any host thread but are not re-entrant on the same workspace;
+ *   - host pointers appear only in vqb_memcpy_async and the vqb_debug_* readers;
  *   - return value: 0 = success, >0 = cudaError_t, <0 = vqb_status below; no C++
  *     exception crosses the boundary;
  *   - activations between layers are NHWC ("pixel rows": (B*H*W, C) row-major); the
