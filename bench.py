@@ -465,6 +465,7 @@ def main():
                        f"{main_mode['depth']} steps in flight",
                 "regions_ms_per_step": main_mode["e2e_regions_ms"],
                 "regions_note": "three timed regions of K steps each; value = the median region (max over ranks)",
+                "l2": "not flushed between end-to-end steps: every step's input arrives from host memory by DMA",
                 "sync_value": main_mode["e2e_sync_value"], "sync_ms_per_step": main_mode["e2e_sync_ms"],
                 "sync_note": "same copies with the caller waiting for each step before submitting the next"},
         "gpu_launches": int(launches_per_step * args.steps),
