@@ -43,6 +43,11 @@ MODEL_CASES = {
     "k1024_s64": dict(h_dim=128, res_h_dim=32, n_res_layers=2, n_embeddings=1024,
                       embedding_dim=64, codebook="normal", codebook_scale=0.05,
                       batch=2, size=64, wseed=8, xseed=9),
+    # BASELINE configs[2] (cfg3) at its real image size: 256x256, K=1024 (B=2 instead of 128).  z_q is not stored
+    # (it is fl(z_e + fl(E[idx] - z_e)) of the stored z_e / idx, quantizer.py:67) to keep the fixture small.
+    "cfg3_s256": dict(h_dim=128, res_h_dim=32, n_res_layers=2, n_embeddings=1024,
+                      embedding_dim=64, codebook="normal", codebook_scale=0.05,
+                      batch=2, size=256, wseed=18, xseed=19, drop=["z_q"]),
 }
 
 # VectorQuantizer-only cases (BASELINE cfg4 grid at a size the CPU finishes in seconds)
@@ -56,6 +61,10 @@ VQ_CASES = {
     # adversarial: duplicated codebook rows (lowest index must win), z equal to a code,
     # one NaN row (argmin returns the NaN column), K=37 / N=3*5*7 ragged sizes
     "vq_adversarial": dict(K=37, D=8, B=3, H=5, W=7, seed=17, kind="adversarial"),
+    # 65 536 rows at the default codebook init (near-tie stress): pins the canonical summation order
+    # against MKL at a size where its blocking could differ.  z_q (16 MB) is stored as a SHA-256 of its bytes.
+    "vq_default_init_64k": dict(K=512, D=64, B=16, H=64, W=64, seed=20, kind="default", hash_zq=True),
+    "vq_k1024_d64_64k": dict(K=1024, D=64, B=16, H=64, W=64, seed=21, kind="normal", hash_zq=True),
 }
 
 _REF_SCRIPT = r"""
@@ -97,7 +106,7 @@ np.savez(job["out"], **out)
 """
 
 
-def make_vq_inputs(K, D, B, H, W, seed, kind):
+def make_vq_inputs(K, D, B, H, W, seed, kind, hash_zq=False):
     """(z NCHW, codebook) for a VectorQuantizer-only case; shared with the tests."""
     rng = np.random.RandomState(seed)
     z = rng.standard_normal((B, D, H, W)).astype(np.float32)
@@ -133,18 +142,30 @@ def _run_ref(job, arrays):
 def main():
     assert os.path.isdir(REF), "needs the reference checkout (authoring container only)"
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases
     for name, c in MODEL_CASES.items():
+        if only and name not in only:
+            continue
         hp = {k: c[k] for k in ("h_dim", "res_h_dim", "n_res_layers", "n_embeddings", "embedding_dim")}
         sd = make_state_dict(seed=c["wseed"], codebook=c["codebook"],
                              codebook_scale=c["codebook_scale"], **hp)
         x = make_images(c["batch"], c["size"], c["xseed"])
         out = _run_ref(dict(kind="model", hp=hp), dict(sd, __x=x))
+        for k in c.get("drop", []):
+            out.pop(k)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), case=json.dumps(c), **out)
         print(name, {k: v.shape for k, v in out.items()}, "codes used", int((out["hist"] > 0).sum()))
     for name, c in VQ_CASES.items():
+        if only and name not in only:
+            continue
         z, E = make_vq_inputs(**c)
         out = _run_ref(dict(kind="vq", K=c["K"], D=c["D"]), dict(z=z, E=E))
         out.pop("onehot_shape")
+        if c.get("hash_zq"):
+            import hashlib
+            zq = np.ascontiguousarray(out.pop("z_q"))
+            out["z_q_sha256"] = np.array(hashlib.sha256(zq.tobytes()).hexdigest())
+            out["idx"] = out["idx"].astype(np.int32)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), case=json.dumps(c), **out)
         print(name, "codes used", int((out["hist"] > 0).sum()))
 

@@ -34,3 +34,30 @@ def build_model(hp, sd, device="cuda"):
               hp["embedding_dim"], 0.25)
     m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
     return m.to(device).eval()
+
+
+def expected_zq(g, E=None):
+    """The reference's z_q (NCHW) of a golden case, or None when only its hash is stored.  Cases that drop z_q to
+    stay small (cfg3_s256) hold z_e and idx, from which z_q = fl(z_e + fl(E[idx] - z_e)) follows (quantizer.py:60,67)."""
+    if "z_q" in g:
+        return g["z_q"]
+    if "z_e" in g and E is not None:
+        z = g["z_e"]
+        B, D, H, W = z.shape
+        rows = np.ascontiguousarray(z.transpose(0, 2, 3, 1)).reshape(-1, D)
+        e = np.asarray(E, dtype=np.float32)[g["idx"].ravel()]
+        zq = (rows + (e - rows).astype(np.float32)).astype(np.float32)
+        return np.ascontiguousarray(zq.reshape(B, H, W, D).transpose(0, 3, 1, 2))
+    return None
+
+
+def assert_zq_matches(g, zq_nchw, E=None):
+    """Bitwise comparison of a z_q (NCHW fp32 array) with the golden case, through the stored array, the
+    reconstruction above, or the stored SHA-256 of the reference's bytes."""
+    import hashlib
+    zq_nchw = np.ascontiguousarray(zq_nchw, dtype=np.float32)
+    want = expected_zq(g, E)
+    if want is not None:
+        assert np.array_equal(zq_nchw, want, equal_nan=True)
+    else:
+        assert hashlib.sha256(zq_nchw.tobytes()).hexdigest() == str(g["z_q_sha256"])

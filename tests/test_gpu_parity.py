@@ -10,8 +10,8 @@ import pytest
 import torch
 
 from oracle import cref
-from tests.helpers import (MODEL_CASES, VQ_CASES, build_model, load_golden, make_vq_inputs,
-                           model_case_inputs)
+from tests.helpers import (MODEL_CASES, VQ_CASES, assert_zq_matches, build_model, expected_zq, load_golden,
+                           make_vq_inputs, model_case_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +37,8 @@ def test_vq_kernel_bit_exact_vs_oracle_and_reference(name):
     assert idx.dtype == torch.int64
     assert np.array_equal(idx.cpu().numpy(), o["idx"])                       # vs oracle
     assert np.array_equal(idx.cpu().numpy(), g["idx"].ravel())               # vs reference
-    assert np.array_equal(zq.cpu().numpy(), o["zq"], equal_nan=True)         # bitwise
+    assert np.array_equal(zq.cpu().numpy(), o["zq"], equal_nan=True)         # bitwise vs oracle
+    assert_zq_matches(g, zq.cpu().numpy().reshape(B, H, W, D).transpose(0, 3, 1, 2))   # bitwise vs reference
     assert np.array_equal(hist.cpu().numpy(), g["hist"])
     np.testing.assert_allclose(sse.item(), o["sse"], rtol=1e-12, equal_nan=True)
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-6, equal_nan=True)
@@ -205,11 +206,12 @@ def test_vqvae_forward_vs_reference_golden(name):
     # VQ boundary: the reference's own z_e in -> bit-exact indices, bitwise z_q
     loss_b, zq_b, perp_b, _, idx_b = m.vector_quantization(_cuda(g["z_e"]))
     assert np.array_equal(idx_b.cpu().numpy(), g["idx"])
-    assert np.array_equal(zq_b.cpu().numpy(), g["z_q"])
+    E_np = sd["vector_quantization.embedding.weight"]
+    assert_zq_matches(g, zq_b.cpu().numpy(), E_np)
     np.testing.assert_allclose(loss_b.item(), g["loss"], rtol=1e-5)
     np.testing.assert_allclose(perp_b.item(), g["perplexity"], rtol=2e-5)
     # decoder on the reference's z_q
-    xh_b = m.decoder(_cuda(g["z_q"]))
+    xh_b = m.decoder(_cuda(expected_zq(g, E_np)))
     np.testing.assert_allclose(xh_b.cpu().numpy(), g["x_hat"], atol=CONV_ATOL, rtol=0)
     # fused forward
     loss, x_hat, perp = m(xc)

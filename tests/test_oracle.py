@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import cref, torch_port
-from tests.helpers import MODEL_CASES, VQ_CASES, load_golden, make_vq_inputs, model_case_inputs
+from tests.helpers import (MODEL_CASES, VQ_CASES, assert_zq_matches, expected_zq, load_golden, make_vq_inputs,
+                           model_case_inputs)
 
 
 @pytest.mark.parametrize("name", sorted(VQ_CASES))
@@ -15,7 +16,7 @@ def test_c_oracle_vq_matches_reference_bit_exact(name):
     r = cref.vq_nchw(z, E)
     assert np.array_equal(r["idx"], g["idx"])                      # int64, bit-exact
     assert r["idx"].dtype == np.int64 and r["idx"].shape == g["idx"].shape
-    assert np.array_equal(r["zq_nchw"], g["z_q"], equal_nan=True)  # fp32 bitwise (Q4)
+    assert_zq_matches(g, r["zq_nchw"])                             # fp32 bitwise (Q4)
     assert np.array_equal(r["hist"], g["hist"])
     np.testing.assert_allclose(r["loss"], g["loss"], rtol=1e-6, equal_nan=True)
     np.testing.assert_allclose(r["perplexity"], g["perplexity"], rtol=2e-5)
@@ -41,7 +42,7 @@ def test_c_oracle_model_matches_reference(name):
     # VQ boundary: same z_e in -> identical indices and bitwise z_q
     b = cref.vq_nchw(g["z_e"], sd["vector_quantization.embedding.weight"])
     assert np.array_equal(b["idx"], g["idx"])
-    assert np.array_equal(b["zq_nchw"], g["z_q"])
+    assert_zq_matches(g, b["zq_nchw"], sd["vector_quantization.embedding.weight"])
     # end to end (oracle convs accumulate in double, the reference in fp32)
     assert np.array_equal(o["idx"], g["idx"])
     np.testing.assert_allclose(o["x_hat"], g["x_hat"], atol=2e-7, rtol=0)
