@@ -91,6 +91,43 @@ int vqb_conv2d_f32(const float *in, const float *w_packed, const float *bias,
                    int kh, int kw, int stride, int pad, int transposed, int in_layout,
                    int out_layout, int relu, int precision, void *stream);
 
+/* ---- bf16 activation path (VQB_BF16): persistent tcgen05 kind::f16 kernels ------------
+ * Between layers the activations are bf16 NHWC; weights are packed to bf16 once per
+ * load_state_dict; accumulation is fp32 in TMEM.  This is the arithmetic the reference
+ * reaches through torch.autocast(dtype=torch.bfloat16) around vqvae.py:29-44.
+ * The layer shapes are named, not parameterised:                                         */
+enum vqb_conv_kind {
+    VQB_CONV_K1 = 0,        /* nn.Conv2d k1 s1 p0           vqvae.py:16-17                 */
+    VQB_CONV_K3 = 1,        /* nn.Conv2d k3 s1 p1           encoder.py:35-36               */
+    VQB_CONVT_K3 = 2,       /* nn.ConvTranspose2d k3 s1 p1  decoder.py:28-29               */
+    VQB_CONV_K4S2 = 3,      /* nn.Conv2d k4 s2 p1           encoder.py:32-33 (H, W even)   */
+    VQB_CONVT_K4S2 = 4,     /* nn.ConvTranspose2d k4 s2 p1  decoder.py:31-32 (Cout % 32 == 0, Cout <= 128) */
+    VQB_CONVT_K4S2_OUT = 5  /* same to Cout <= 4 channels, fp32 NCHW output: decoder.py:34-35 */
+};
+/* Bytes of the packed bf16 weight of one layer (0 = shape not covered: Cin % 64 != 0, ...). */
+size_t vqb_conv_bf16_packed_bytes(int kind, int Cout, int Cin);
+/* w: the layer's fp32 weight as PyTorch stores it ((Cout,Cin,kh,kw), or (Cin,Cout,kh,kw) for
+ * the transposed kinds) -> `packed` (128-byte aligned): one 128-byte row of 64 input channels
+ * per (k-step, output column), in the order the kernel's k-steps consume them.            */
+int vqb_pack_conv_weight_bf16(const float *w, void *packed, int kind, int Cout, int Cin,
+                              void *stream);
+/* One layer forward on bf16 NHWC input (B,H,W,Cin):  out = act(conv(in) + bias).
+ * out: bf16 NHWC, or fp32 NHWC when out_f32 != 0 (z_e for the bit-exact VQ), or fp32 NCHW
+ * (B,Cout,2H,2W) for VQB_CONVT_K4S2_OUT.  All pointers 16-byte aligned.                   */
+int vqb_conv2d_bf16(const void *in, const void *packed, const float *bias, void *out, int B,
+                    int Cin, int H, int W, int Cout, int kind, int relu, int out_f32,
+                    void *stream);
+
+/* One ResidualLayer application on bf16 NHWC activations (residual.py:18-29 as evaluated,
+ * SURVEY Q2):  out = act( r + W2 . relu( W1 (*) r ) ),  act = ReLU iff relu_out.
+ * w1_packed: vqb_pack_conv_weight_bf16(kind VQB_CONV_K3, Cout = Cmid, Cin = C) of res_block.1.weight;
+ * w2_packed: vqb_pack_conv_weight_bf16(kind VQB_RES_W2 = 6, Cout = C, Cin = Cmid) of res_block.3.weight.
+ * One persistent tcgen05 kernel: both GEMMs chained per tile, W1 and W2 resident in shared memory.
+ * C in {64, 128}, Cmid % 16 == 0, Cmid <= 64; other shapes return VQB_ERR_UNSUPPORTED.      */
+#define VQB_RES_W2 6
+int vqb_residual_layer_bf16(const void *r, const void *w1_packed, const void *w2_packed, void *out,
+                            int B, int H, int W, int C, int Cmid, int relu_out, void *stream);
+
 /* ---- one ResidualLayer application, residual.py:18-29 -----------------------------
  * As the reference evaluates it (the in-place ReLU of :19 has already replaced x by
  * r = relu(x)):   out = act( r + W2 . relu( W1 (*) r ) )

@@ -1,0 +1,111 @@
+"""VQB_BF16 path: the persistent tcgen05 kind::f16 kernels (hconv.cu, res_bf16.cu) against the C oracle.
+
+Operands are rounded to bf16 (8-bit mantissa) and accumulated in fp32, so each kernel is compared with the oracle
+evaluated on the SAME bf16-rounded inputs and weights: what is left is the fp32 accumulation order (~1e-5) plus, for
+bf16 outputs, one rounding of the result (relative 2^-9).  Tolerances: bf16 outputs rtol 2^-8 + atol 2e-3, fp32
+outputs atol 2e-4.  Needs a B200 (``-m gpu``).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(a):
+    """Round an fp32 array to bf16 and back (the operand precision of the kernels)."""
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+def _nhwc_bf16(x_nchw):
+    return torch.from_numpy(np.ascontiguousarray(x_nchw.transpose(0, 2, 3, 1))).to(torch.bfloat16).cuda().contiguous()
+
+
+def _run_layer(rng, B, Cin, H, W, Cout, k, stride, transposed, relu, out_f32):
+    from vqvae_b200 import ops
+    from vqvae_b200 import _lib
+    x = _bf(rng.standard_normal((B, Cin, H, W)).astype(np.float32))
+    wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+    w = (rng.standard_normal(wshape) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    pad = 0 if k == 1 else 1
+    wq = _bf(w)
+    ref = cref.conv_transpose2d(x, wq, b, stride, pad) if transposed else cref.conv2d(x, wq, b, stride, pad)
+    if relu:
+        ref = np.maximum(ref, 0)
+    kind = ops.conv_kind(k, stride, transposed, Cout)
+    assert kind is not None
+    packed = ops.pack_conv_weight_bf16(torch.from_numpy(w).cuda(), kind)
+    assert packed is not None
+    y = ops.conv2d_bf16(_nhwc_bf16(x), packed, torch.from_numpy(b).cuda(), B=B, Cin=Cin, H=H, W=W, Cout=Cout, kind=kind,
+                        relu=relu, out_f32=out_f32)
+    torch.cuda.synchronize()
+    y = y.float().cpu().numpy()
+    if kind != _lib.CONVT_K4S2_OUT:
+        y = y.transpose(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    if out_f32 or kind == _lib.CONVT_K4S2_OUT:
+        np.testing.assert_allclose(y, ref, atol=2e-4, rtol=1e-4)
+    else:
+        np.testing.assert_allclose(y, ref, atol=2e-3, rtol=2.0 ** -8)
+
+
+BF16_LAYER_CASES = [
+    # B, Cin, H, W, Cout, k, stride, transposed, relu, out_f32          (reference layer)
+    (2, 128, 16, 32, 128, 3, 1, False, True, False),    # encoder.py:35-36, two M-tiles per weight stage
+    (1, 128, 64, 64, 128, 3, 1, False, False, False),   # same at the cfg3 latent size (32 tiles)
+    (3, 128, 8, 8, 128, 3, 1, False, True, False),      # cfg2 latent size: TW = 8, two images per tile
+    (2, 64, 20, 36, 128, 3, 1, True, True, False),      # decoder.py:28-29, ragged tiles in x and y
+    (2, 64, 32, 32, 128, 4, 2, False, True, False),     # encoder.py:32-34 (space-to-depth planes)
+    (1, 64, 128, 128, 128, 4, 2, False, True, False),   # same, cfg3 size
+    (3, 64, 16, 16, 128, 4, 2, False, False, False),    # cfg2 size
+    (2, 128, 16, 16, 64, 4, 2, True, True, False),      # decoder.py:31-33: two passes, paired column parities
+    (1, 128, 64, 64, 64, 4, 2, True, True, False),      # cfg3 size
+    (3, 128, 8, 8, 64, 4, 2, True, False, False),       # cfg2 size
+    (2, 128, 16, 32, 64, 1, 1, False, False, True),     # vqvae.py:16-17 -> fp32 z_e, resident weights
+    (5, 128, 8, 8, 64, 1, 1, False, False, True),       # cfg2 size, ragged batch (5 images, 2 per tile)
+    (2, 64, 32, 32, 3, 4, 2, True, False, True),        # decoder.py:34-35 -> fp32 NCHW, pixel shuffle
+    (1, 64, 128, 128, 3, 4, 2, True, False, True),      # cfg3 size
+    (3, 64, 16, 16, 3, 4, 2, True, True, True),         # cfg2 size
+    (1, 64, 12, 20, 48, 3, 1, False, True, False),      # Cout = 48 (16-column tail group), ragged
+    (1, 256, 16, 16, 64, 3, 1, False, False, False),    # four 64-channel chunks
+]
+
+
+@pytest.mark.parametrize("case", BF16_LAYER_CASES)
+def test_bf16_conv_layers_vs_oracle(case):
+    rng = np.random.RandomState(abs(hash(case)) % (2 ** 31))
+    _run_layer(rng, *case)
+
+
+def test_bf16_conv_many_tiles_persistent_loop():
+    """More tiles than SMs: every CTA walks several tiles (ring wrap-around, TMEM double buffering)."""
+    rng = np.random.RandomState(7)
+    _run_layer(rng, 8, 128, 64, 64, 128, 3, 1, False, True, False)        # 512 tiles of 256 pixels
+    _run_layer(rng, 4, 128, 64, 64, 64, 4, 2, True, True, False)          # 2 passes x 256 tiles
+
+
+@pytest.mark.parametrize("B,H,W,C,Cmid,relu_out", [(2, 16, 32, 128, 32, True), (1, 64, 64, 128, 32, True), (3, 8, 8, 128, 32, True),
+                                                   (2, 20, 36, 128, 32, False), (5, 8, 8, 64, 16, True), (6, 64, 64, 128, 32, True)])
+def test_bf16_residual_layer_vs_oracle(B, H, W, C, Cmid, relu_out):
+    """res_bf16.cu: out = act(r + W2.relu(W1 (*) r)) with bf16 operands; the intermediate relu(W1 (*) r) is rounded
+    to bf16 before the second GEMM (it is that GEMM's A operand), which the oracle side mirrors."""
+    from vqvae_b200 import ops, _lib
+    rng = np.random.RandomState(B * 1000 + H * 100 + C)
+    r = _bf(np.maximum(rng.standard_normal((B, C, H, W)).astype(np.float32), 0))
+    w1 = (rng.standard_normal((Cmid, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32)
+    w2 = (rng.standard_normal((C, Cmid, 1, 1)) / np.sqrt(Cmid)).astype(np.float32)
+    mid = _bf(np.maximum(cref.conv2d(r, _bf(w1), None, 1, 1), 0))
+    ref = r + cref.conv2d(mid, _bf(w2), None, 1, 0)
+    if relu_out:
+        ref = np.maximum(ref, 0)
+    p1 = ops.pack_conv_weight_bf16(torch.from_numpy(w1).cuda(), _lib.CONV_K3)
+    p2 = ops.pack_conv_weight_bf16(torch.from_numpy(w2).cuda(), _lib.RES_W2)
+    y = ops.residual_layer_bf16(_nhwc_bf16(r), p1, p2, B=B, H=H, W=W, C=C, Cmid=Cmid, relu_out=relu_out)
+    torch.cuda.synchronize()
+    y = y.float().cpu().numpy().transpose(0, 3, 1, 2)
+    # a mid value that sits on a bf16 rounding boundary may round the other way (fp32 accumulation order): one such
+    # flip moves an output by 2^-9 |mid| |w2| ~ 1e-3, hence the absolute term
+    np.testing.assert_allclose(y, ref, atol=6e-3, rtol=2.0 ** -7)

@@ -1,0 +1,619 @@
+// hconv.cu -- persistent tcgen05 implicit-GEMM convolution on bf16 activations (VQB_BF16 mode), sm_100a.
+//
+// One kernel for every tensor-core conv layer of the hot path when the activations between layers are bf16 NHWC:
+//   encoder.py:32-34  Conv2d k4 s2 p1        (space-to-depth view: a 2x2-tap conv on four parity planes)
+//   encoder.py:35-36  Conv2d k3 s1 p1
+//   vqvae.py:16-17    Conv2d k1               (fp32 output: z_e feeds the bit-exact VQ)
+//   decoder.py:28-29  ConvTranspose2d k3 s1 p1
+//   decoder.py:31-33  ConvTranspose2d k4 s2 p1 (two passes = output row parities; each pass accumulates both output
+//                                               column parities side by side: shift dx = 0 feeds both -> one N = 2 Cout MMA)
+//   decoder.py:34-35  ConvTranspose2d k4 s2 p1 to <= 4 channels (one 3x3-neighbourhood GEMM, N = 16, pixel-shuffle
+//                                               epilogue writing the NCHW fp32 module output)
+//
+// Shape of the kernel (measured facts behind it: profiles/r02_ubench_mma_rate.txt, r02_ubench_l2_stream.txt):
+//   * ONE CTA per SM, persistent over tiles of TW x BH x BN pixels (TW = 16 -> two M = 128 tiles that share every
+//     weight stage; 8 when the image is narrower).  An M128 N128 K16 bf16 MMA issued from one converged warp runs at
+//     the 64-cycle floor from a single CTA (8158 flop/cycle/SM), so no cta_group::2 is needed for peak; N = 64 costs
+//     48 cycles and N = 32 costs 40, which is why the k4s2 transposed conv pairs its column parities.
+//   * the input tile is loaded ONCE per 64-channel chunk with its 1-pixel halo (5-D TMA box, 128-byte swizzle) and
+//     the taps are shifted UMMA descriptors into it (conv_halo.cu's trick; the swizzle phase comes from absolute
+//     shared-memory address bits so operand windows may start on any 128-byte row).  No im2col anywhere.
+//   * weights stream through a ring of 16 KB stages (one L2-resident weight set read by all SMs streams at
+//     121 GB/s per SM, 18 TB/s chip-wide; a 256-pixel tile needs 61 GB/s at the full MMA rate) -- or stay resident
+//     when the whole set fits the ring.
+//   * fp32 accumulators double-buffered in TMEM (2 x 256 columns): 8 epilogue warps drain tile t (tcgen05.ld ->
+//     +bias -> ReLU -> bf16 pack -> 16-byte NHWC stores) under the MMAs of tile t+1.
+//   * warps: 0 = halo producer, 1 = MMA issuer (converged warp, elected lane), 2 = TMEM allocator, 3 = weight
+//     producer, 4-11 = epilogue.
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "bf16_common.cuh"
+
+namespace {
+
+constexpr int HC_THREADS = 384;
+constexpr int HC_MAX_STEPS = 40;      // per pass
+constexpr int HC_MAX_STAGES = 40;
+constexpr int HC_MAX_CHUNKS = 8;
+constexpr int HC_MAX_HB = 3;
+
+enum { ST_FIRST = 1, ST_NEWCHUNK = 2, ST_ENDCHUNK = 4, ST_HALFBOX = 8 };
+enum { EPI_NHWC = 0, EPI_SHUFFLE_NCHW = 1 };
+
+struct HStep {
+    uint32_t a_off16;      // tap offset inside the halo tile, 16-byte units (M-tile 0)
+    uint16_t w_row;        // first row of this step's weight tile in the packed matrix
+    uint8_t nb8;           // MMA N / 8
+    uint8_t d_col;         // accumulator column offset inside the M-tile's column block
+    uint8_t flags;
+    uint8_t pad[3];
+};
+
+struct HParams {
+    const float *bias;
+    void *out;
+    int B, H, W;                    // the GEMM's pixel grid (= input grid of a stride-1 / s2d view)
+    int TW, BH, BN, MT, WP, halo;
+    int tiles_x, tiles_y, tiles_n, npass;
+    long long ntiles;
+    int NCOL;                       // accumulator columns per M-tile
+    int nsteps[2], nchunks;
+    int chunk_c0[HC_MAX_CHUNKS], chunk_p[HC_MAX_CHUNKS];
+    int S, wst_bytes, resident, nhb, halo_bytes, halo_stride;
+    int epi_mode, cg, sy, sx, OH, OW, Cout, relu, out_f32, bias_mod;
+    HStep steps[2][HC_MAX_STEPS];
+};
+
+__global__ void __launch_bounds__(HC_THREADS, 1)
+hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
+             const __grid_constant__ CUtensorMap tma_wh, const __grid_constant__ HParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+
+    const uint32_t ring_off = (uint32_t)(p.nhb * p.halo_stride);
+    const uint32_t bar_off = ring_off + (uint32_t)(p.S * p.wst_bytes);
+    const uint32_t bars = sbase + bar_off;
+    auto wfull = [&](int s) { return bars + 8u * s; };
+    auto wempty = [&](int s) { return bars + 8u * (HC_MAX_STAGES + s); };
+    auto hfull = [&](int b) { return bars + 8u * (2 * HC_MAX_STAGES + b); };
+    auto hempty = [&](int b) { return bars + 8u * (2 * HC_MAX_STAGES + HC_MAX_HB + b); };
+    auto tfull = [&](int a) { return bars + 8u * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + a); };
+    auto tempty = [&](int a) { return bars + 8u * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 2 + a); };
+    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + MISC);
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + MISC + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid < p.S) { ptx::mbar_init(wfull(tid), 1); ptx::mbar_init(wempty(tid), 1); }
+    if (tid >= 64 && tid < 64 + p.nhb) { ptx::mbar_init(hfull(tid - 64), 1); ptx::mbar_init(hempty(tid - 64), 1); }
+    if (tid >= 96 && tid < 98) { ptx::mbar_init(tfull(tid - 96), 1); ptx::mbar_init(tempty(tid - 96), 8); }
+    if (tid == 128) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w); ptx::prefetch_tmap(&tma_wh); }
+    ptx::fence_mbar_init();
+    for (int c = tid; c < p.NCOL; c += HC_THREADS) {
+        float b = 0.f;
+        if (p.bias) {
+            if (p.epi_mode == EPI_SHUFFLE_NCHW) b = c < 4 * p.bias_mod ? __ldg(p.bias + c % p.bias_mod) : 0.f;
+            else b = __ldg(p.bias + c % p.bias_mod);
+        }
+        bias_s[c] = b;
+    }
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + MISC, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();
+
+    const long long ntiles = p.ntiles;
+    const int G = (int)gridDim.x;
+
+    if (warp == 0) {
+        // ===================== halo producer =====================
+        const bool leader = ptx::elect_one();
+        pdl_wait();                                  // the input activation is the previous layer's output
+        uint32_t hb = 0, hpar = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+            long long t = tile / p.npass;
+            const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
+            const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
+            const int gx0 = tx * p.TW, gy0 = ty * p.BH, n0 = (int)t * p.BN;
+            for (int k = 0; k < p.nchunks; ++k) {
+                ptx::mbar_wait(hempty((int)hb), hpar ^ 1);
+                if (leader) {
+                    ptx::mbar_expect_tx(hfull((int)hb), (uint32_t)p.halo_bytes);
+                    tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), p.chunk_c0[k], gx0 - p.halo, n0,
+                                p.chunk_p[k], gy0 - p.halo);
+                }
+                if (++hb == (uint32_t)p.nhb) { hb = 0; hpar ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer =====================
+        const bool leader = ptx::elect_one();
+        if (p.resident) {
+            int s = 0;
+            for (int ps = 0; ps < p.npass; ++ps)
+                for (int i = 0; i < p.nsteps[ps]; ++i, ++s) {
+                    const HStep st = p.steps[ps][i];
+                    if (leader) {
+                        ptx::mbar_expect_tx(wfull(s), (uint32_t)st.nb8 * 8u * 128u);
+                        ptx::tma_load_2d(sbase + ring_off + (uint32_t)(s * p.wst_bytes), (st.flags & ST_HALFBOX) ? &tma_wh : &tma_w,
+                                         wfull(s), 0, (int)st.w_row);
+                    }
+                }
+        } else {
+            uint32_t ws = 0, wpar = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+                const int ps = (int)(tile % p.npass);
+                const int ns = p.nsteps[ps];
+                for (int i = 0; i < ns; ++i) {
+                    const HStep st = p.steps[ps][i];
+                    ptx::mbar_wait(wempty((int)ws), wpar ^ 1);
+                    if (leader) {
+                        ptx::mbar_expect_tx(wfull((int)ws), (uint32_t)st.nb8 * 8u * 128u);
+                        ptx::tma_load_2d(sbase + ring_off + ws * (uint32_t)p.wst_bytes, (st.flags & ST_HALFBOX) ? &tma_wh : &tma_w,
+                                         wfull((int)ws), 0, (int)st.w_row);
+                    }
+                    if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = ptx::elect_one();
+        const uint32_t a_hi = ptx::desc_hi_sw128((uint32_t)(p.WP * 128)), b_hi = ptx::desc_hi_sw128(1024);
+        const uint32_t ring16 = (sbase + ring_off) >> 4, wst16 = (uint32_t)p.wst_bytes >> 4;
+        const uint32_t halo16 = sbase >> 4, hstride16 = (uint32_t)p.halo_stride >> 4;
+        uint32_t hb = 0, hpar = 0, ws = 0, wpar = 0;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+            const int ps = (int)(tile % p.npass);
+            const int ns = p.nsteps[ps];
+            const int acc = it & 1;
+            ptx::mbar_wait(tempty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+            ptx::tc_fence_after();
+            const uint32_t dbase = tmem_base + (uint32_t)(acc * 256);
+            int sres = ps == 0 ? 0 : p.nsteps[0];            // resident mode: stage = global step index
+            for (int i = 0; i < ns; ++i) {
+                const HStep st = p.steps[ps][i];
+                if (st.flags & ST_NEWCHUNK) ptx::mbar_wait(hfull((int)hb), hpar);
+                uint32_t stage;
+                if (p.resident) {
+                    stage = (uint32_t)(sres + i);
+                    if (it < 2) ptx::mbar_wait(wfull((int)stage), 0);            // each pass first occurs at it <= 1
+                } else {
+                    stage = ws;
+                    ptx::mbar_wait(wfull((int)ws), wpar);
+                }
+                ptx::tc_fence_after();
+                const uint32_t idesc = ptx::instr_desc(ptx::FMT_BF16, 128, (uint32_t)st.nb8 * 8u);
+                const uint32_t a_lo = halo16 + hb * hstride16 + st.a_off16;
+                const uint32_t b_lo = ring16 + stage * wst16;
+                const uint32_t d0 = dbase + (uint32_t)st.d_col;
+                uint32_t accf = (st.flags & ST_FIRST) ? 0u : 1u;
+                for (int m = 0; m < p.MT; ++m) {
+                    uint32_t af = accf;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (leader) mma_bf16_w(d0 + (uint32_t)(m * p.NCOL), a_lo + (uint32_t)(m * 64) + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, af);
+                        af = 1u;
+                    }
+                }
+                if (!p.resident) {
+                    if (leader) ptx::tc_commit(wempty((int)ws));
+                    if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                }
+                if (st.flags & ST_ENDCHUNK) {
+                    if (leader) ptx::tc_commit(hempty((int)hb));
+                    if (++hb == (uint32_t)p.nhb) { hb = 0; hpar ^= 1; }
+                }
+                __syncwarp();
+            }
+            if (leader) ptx::tc_commit(tfull(acc));
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3, g = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int em = p.MT == 2 ? g : 0;
+        const int ncol_thr = p.MT == 2 ? p.NCOL : (p.NCOL >= 64 ? p.NCOL / 2 : (g == 0 ? p.NCOL : 0));
+        const int c_lo = (p.MT == 2 || p.NCOL < 64) ? 0 : g * (p.NCOL / 2);
+        const int xx = row & 7, grp = row >> 3;
+        const int bn = grp % p.BN, yy = grp / p.BN;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+            long long t = tile;
+            const int ps = (int)(t % p.npass); t /= p.npass;
+            const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
+            const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
+            const int gx = tx * p.TW + em * 8 + xx, gy = ty * p.BH + yy, n = (int)t * p.BN + bn;
+            const bool valid = gx < p.W && gy < p.H && n < p.B;
+            const int acc = it & 1;
+            ptx::mbar_wait(tfull(acc), (uint32_t)((it >> 1) & 1));
+            ptx::tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + em * p.NCOL);
+            if (p.epi_mode == EPI_SHUFFLE_NCHW) {
+                // decoder.py:34-35: column (py*2+px)*Cout+co of input pixel (gy,gx) is output pixel (2gy+py, 2gx+px),
+                // channel co, of the NCHW fp32 module output
+                if (ncol_thr > 0) {
+                    float v[16];
+                    tmem_ld16(trow, v);
+                    if (valid) {
+                        const int co_n = p.Cout;
+                        float *o = reinterpret_cast<float *>(p.out);
+                        for (int co = 0; co < co_n; ++co)
+#pragma unroll
+                            for (int py = 0; py < 2; ++py) {
+                                float2 w2 = make_float2(v[(py * 2 + 0) * co_n + co] + bias_s[co], v[(py * 2 + 1) * co_n + co] + bias_s[co]);
+                                if (p.relu) { w2.x = fmaxf(w2.x, 0.f); w2.y = fmaxf(w2.y, 0.f); }
+                                *reinterpret_cast<float2 *>(o + (((long long)n * co_n + co) * p.OH + 2 * gy + py) * p.OW + 2 * gx) = w2;
+                            }
+                    }
+                }
+            } else {
+                // NHWC store; column group j (cg columns) is output pixel (gy*sy + pass, gx*sx + j)
+                const long long prow = ((long long)n * p.OH + (long long)gy * p.sy + ps) * p.OW + (long long)gx * p.sx;
+                float va[32], vb[32];
+                auto emit = [&](const float (&v)[32], int c0, int nc) {       // nc = live columns of this group (16 or 32)
+                    if (!valid) return;
+                    const int j = c0 / p.cg, cc = c0 - j * p.cg;
+                    const long long off = (prow + j) * p.Cout + cc;
+                    if (p.out_f32) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (i < nc) {
+                                const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
+                                float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+                                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                dst[i >> 2] = o;
+                            }
+                        }
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            if (i < nc) {
+                                float o[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    o[u] = v[i + u] + bias_s[c0 + i + u];
+                                    if (p.relu) o[u] = fmaxf(o[u], 0.f);
+                                }
+                                dst[i >> 3] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                            }
+                        }
+                    }
+                };
+                // the TMEM load of the next 32 columns travels while the current ones are stored
+                if (ncol_thr > 0) {
+                    const int c_hi = c_lo + ncol_thr;
+                    ptx::tmem_ld32(trow + (uint32_t)c_lo, va);
+                    for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+                        ptx::tmem_ld_wait32(va);
+                        if (c0 + 32 < c_hi) ptx::tmem_ld32(trow + (uint32_t)(c0 + 32), vb);
+                        emit(va, c0, c_hi - c0);
+                        if (c0 + 32 < c_hi) {
+                            ptx::tmem_ld_wait32(vb);
+                            if (c0 + 64 < c_hi) ptx::tmem_ld32(trow + (uint32_t)(c0 + 64), va);
+                            emit(vb, c0 + 32, c_hi - c0 - 32);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty(acc));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side: plans
+struct RowDesc { int co, ci0, r, s; };          // one packed weight row = 64 input channels of (co, r, s); co < 0: zeros
+
+struct PlanStep { int chunk, dy, dx, nb, d_col, w_row, flags; };
+
+struct Plan {
+    int kind = -1, Cin = 0, Cout = 0;
+    int nchunks = 0, chunk_c0[HC_MAX_CHUNKS], chunk_p[HC_MAX_CHUNKS];
+    int npass = 1, nsteps[2] = {0, 0};
+    PlanStep steps[2][HC_MAX_STEPS];
+    int NCOL = 0, nbmax = 0, nbhalf = 0, halo = 1, epi_mode = EPI_NHWC, cg = 0, sy = 1, sx = 1, transposed = 0, s2d = 0;
+    std::vector<RowDesc> rows;
+};
+
+void add_step(Plan &pl, int pass, int chunk, int dy, int dx, int nb, int d_col, int w_row, bool half) {
+    PlanStep &s = pl.steps[pass][pl.nsteps[pass]++];
+    s.chunk = chunk; s.dy = dy; s.dx = dx; s.nb = nb; s.d_col = d_col; s.w_row = w_row; s.flags = half ? ST_HALFBOX : 0;
+}
+
+// returns false when the shape is outside what this kernel family covers
+bool build_plan(Plan &pl, int kind, int Cin, int Cout) {
+    pl = Plan();
+    pl.kind = kind; pl.Cin = Cin; pl.Cout = Cout;
+    if (kind == VQB_RES_W2_KIND) {
+        // residual.py:23: 1x1 conv Cmid -> C; one K chunk, rows beyond Cin are zero (the pack kernel pads)
+        if (Cin < 16 || Cin > 64 || Cin % 16 != 0 || Cout % 16 != 0 || Cout < 16 || Cout > 256) return false;
+        pl.nchunks = 1; pl.chunk_c0[0] = 0; pl.chunk_p[0] = 0; pl.NCOL = Cout; pl.nbmax = Cout; pl.cg = Cout; pl.halo = 0;
+        for (int c = 0; c < Cout; ++c) pl.rows.push_back({c, 0, 0, 0});
+        pl.nsteps[0] = 1;
+        PlanStep &st = pl.steps[0][0];
+        st.chunk = 0; st.dy = 0; st.dx = 0; st.nb = Cout; st.d_col = 0; st.w_row = 0; st.flags = ST_FIRST | ST_NEWCHUNK | ST_ENDCHUNK;
+        return true;
+    }
+    if (Cin % 64 != 0 || Cin < 64) return false;
+    const int kc = Cin / 64;
+    auto rows_for = [&](int co0, int nco, int ci0, int r, int s) {
+        const int row0 = (int)pl.rows.size();
+        for (int c = 0; c < nco; ++c) pl.rows.push_back({co0 + c, ci0, r, s});
+        return row0;
+    };
+    switch (kind) {
+        case VQB_CONV_K3: case VQB_CONVT_K3: case VQB_CONV_K1: {
+            if (Cout % 16 != 0 || Cout < 16 || Cout > 256 || kc > HC_MAX_CHUNKS) return false;
+            const int taps = kind == VQB_CONV_K1 ? 1 : 9;
+            if (kc * taps > HC_MAX_STEPS) return false;
+            pl.transposed = kind == VQB_CONVT_K3;
+            pl.halo = kind == VQB_CONV_K1 ? 0 : 1;
+            pl.nchunks = kc; pl.NCOL = Cout; pl.nbmax = Cout; pl.cg = Cout;
+            for (int k = 0; k < kc; ++k) {
+                pl.chunk_c0[k] = 64 * k; pl.chunk_p[k] = 0;
+                for (int t = 0; t < taps; ++t) {
+                    const int r = taps == 1 ? 0 : t / 3, s = taps == 1 ? 0 : t % 3;
+                    const int dy = taps == 1 ? 0 : (pl.transposed ? 1 - r : r - 1), dx = taps == 1 ? 0 : (pl.transposed ? 1 - s : s - 1);
+                    add_step(pl, 0, k, dy, dx, Cout, 0, rows_for(0, Cout, 64 * k, r, s), false);
+                }
+            }
+            break;
+        }
+        case VQB_CONV_K4S2: {
+            // encoder.py:32: out(y) reads in(2y + r - 1): r = 0 -> (Y = y-1, parity 1), 1 -> (y, 0), 2 -> (y, 1), 3 -> (y+1, 0)
+            if (Cout % 16 != 0 || Cout < 16 || Cout > 256 || 4 * kc > HC_MAX_CHUNKS || 16 * kc > HC_MAX_STEPS) return false;
+            pl.s2d = 1; pl.NCOL = Cout; pl.nbmax = Cout; pl.cg = Cout;
+            static const int RR[2][2] = {{1, 3}, {0, 2}}, DD[2][2] = {{0, 1}, {-1, 0}};      // [parity][i] -> kernel row / shift
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    for (int k = 0; k < kc; ++k) {
+                        const int ch = pl.nchunks++;
+                        pl.chunk_c0[ch] = px * Cin + 64 * k; pl.chunk_p[ch] = py;
+                        for (int a = 0; a < 2; ++a)
+                            for (int b = 0; b < 2; ++b)
+                                add_step(pl, 0, ch, DD[py][a], DD[px][b], Cout, 0, rows_for(0, Cout, 64 * k, RR[py][a], RR[px][b]), false);
+                    }
+            break;
+        }
+        case VQB_CONVT_K4S2: {
+            // decoder.py:31: output row 2y+py takes input row y+dy through kernel row r = py + 1 - 2 dy:
+            //   py = 0: (dy 0, r 1), (dy -1, r 3);  py = 1: (dy 0, r 2), (dy +1, r 0); same along x.
+            if (Cout % 32 != 0 || Cout < 32 || 2 * Cout > 256 || kc > HC_MAX_CHUNKS || 6 * kc > HC_MAX_STEPS) return false;
+            pl.transposed = 1; pl.npass = 2; pl.nchunks = kc; pl.NCOL = 2 * Cout; pl.nbmax = 2 * Cout; pl.nbhalf = Cout;
+            pl.cg = Cout; pl.sy = 2; pl.sx = 2;
+            static const int TR[2][2] = {{1, 3}, {2, 0}}, TD[2][2] = {{0, -1}, {0, 1}};
+            for (int k = 0; k < kc; ++k) { pl.chunk_c0[k] = 64 * k; pl.chunk_p[k] = 0; }
+            for (int py = 0; py < 2; ++py)
+                for (int k = 0; k < kc; ++k)
+                    for (int a = 0; a < 2; ++a) {
+                        const int r = TR[py][a], dy = TD[py][a];
+                        // dx = 0 feeds both column parities: [px 0 with s = 1 | px 1 with s = 2] -> one N = 2 Cout step
+                        const int row0 = rows_for(0, Cout, 64 * k, r, 1);
+                        rows_for(0, Cout, 64 * k, r, 2);
+                        add_step(pl, py, k, dy, 0, 2 * Cout, 0, row0, false);
+                        add_step(pl, py, k, dy, -1, Cout, 0, rows_for(0, Cout, 64 * k, r, 3), true);       // px 0, s = 3
+                        add_step(pl, py, k, dy, 1, Cout, Cout, rows_for(0, Cout, 64 * k, r, 0), true);     // px 1, s = 0
+                    }
+            break;
+        }
+        case VQB_CONVT_K4S2_OUT: {
+            // decoder.py:34: 16 columns (py, px, co); shift (dy,dx) reaches column (py,px,co) through r = py+1-2dy, s = px+1-2dx
+            if (Cout < 1 || Cout > 4 || kc > HC_MAX_CHUNKS || 9 * kc > HC_MAX_STEPS) return false;
+            pl.transposed = 1; pl.nchunks = kc; pl.NCOL = 16; pl.nbmax = 16; pl.cg = 16; pl.epi_mode = EPI_SHUFFLE_NCHW;
+            for (int k = 0; k < kc; ++k) {
+                pl.chunk_c0[k] = 64 * k; pl.chunk_p[k] = 0;
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3 - 1, dx = t % 3 - 1;
+                    const int row0 = (int)pl.rows.size();
+                    for (int col = 0; col < 16; ++col) {
+                        const int ph = col / Cout, co = col % Cout, py = ph >> 1, px = ph & 1;
+                        const int r = py + 1 - 2 * dy, s = px + 1 - 2 * dx;
+                        if (ph < 4 && r >= 0 && r <= 3 && s >= 0 && s <= 3) pl.rows.push_back({co, 64 * k, r, s});
+                        else pl.rows.push_back({-1, 0, 0, 0});
+                    }
+                    add_step(pl, 0, k, dy, dx, 16, 0, row0, false);
+                }
+            }
+            break;
+        }
+        default: return false;
+    }
+    if (pl.rows.size() > 65535) return false;
+    // flags: first write of each accumulator range, chunk boundaries
+    for (int ps = 0; ps < pl.npass; ++ps) {
+        bool seen[256] = {false};
+        for (int i = 0; i < pl.nsteps[ps]; ++i) {
+            PlanStep &s = pl.steps[ps][i];
+            bool first = !seen[s.d_col];
+            for (int c = s.d_col; c < s.d_col + s.nb; ++c) {
+                if (first && seen[c]) return false;          // a partially written range cannot be overwritten
+                if (!first && !seen[c]) return false;
+            }
+            if (first) { s.flags |= ST_FIRST; for (int c = s.d_col; c < s.d_col + s.nb; ++c) seen[c] = true; }
+            if (i == 0 || pl.steps[ps][i - 1].chunk != s.chunk) s.flags |= ST_NEWCHUNK;
+            if (i + 1 == pl.nsteps[ps] || pl.steps[ps][i + 1].chunk != s.chunk) s.flags |= ST_ENDCHUNK;
+        }
+    }
+    return true;
+}
+
+const Plan *get_plan(int kind, int Cin, int Cout) {
+    static std::vector<Plan *> cache;           // a handful of layer shapes per process; never freed
+    for (Plan *pl : cache) if (pl->kind == kind && pl->Cin == Cin && pl->Cout == Cout) return pl;
+    Plan *pl = new Plan();
+    if (!build_plan(*pl, kind, Cin, Cout)) { delete pl; return nullptr; }
+    cache.push_back(pl);
+    return pl;
+}
+
+__global__ void hconv_pack_kernel(const float *__restrict__ w, const int4 *__restrict__ rows, int nrows, int Cout, int Cin,
+                                  int kh, int kw, int transposed, __nv_bfloat16 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * 64) return;
+    const int row = i >> 6, j = i & 63;
+    const int4 d = rows[row];
+    float v = 0.f;
+    if (d.x >= 0 && d.y + j < Cin) {
+        const int ci = d.y + j;
+        v = transposed ? w[(((size_t)ci * Cout + d.x) * kh + d.z) * kw + d.w] : w[(((size_t)d.x * Cin + ci) * kh + d.z) * kw + d.w];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+int pow2_ceil_h(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+void kernel_dims(int kind, int &kh, int &kw) {
+    kh = kw = (kind == VQB_CONV_K1 || kind == VQB_RES_W2_KIND) ? 1 : (kind == VQB_CONV_K3 || kind == VQB_CONVT_K3) ? 3 : 4;
+}
+
+}  // namespace
+
+int hconv_plan_rows(int kind, int Cin, int Cout) {
+    const Plan *pl = get_plan(kind, Cin, Cout);
+    return pl ? (int)pl->rows.size() : -1;
+}
+
+extern "C" size_t vqb_conv_bf16_packed_bytes(int kind, int Cout, int Cin) {
+    const Plan *pl = get_plan(kind, Cin, Cout);
+    if (!pl) return 0;
+    return pl->rows.size() * 128 + pl->rows.size() * sizeof(int4) + 256;
+}
+
+extern "C" int vqb_pack_conv_weight_bf16(const float *w, void *packed, int kind, int Cout, int Cin, void *stream) {
+    if (!w || !packed) return VQB_ERR_BAD_ARG;
+    const Plan *pl = get_plan(kind, Cin, Cout);
+    if (!pl) return VQB_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(packed) & 127) return VQB_ERR_ALIGNMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nrows = (int)pl->rows.size();
+    int4 *table = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(packed) + (size_t)nrows * 128);
+    static_assert(sizeof(RowDesc) == sizeof(int4), "row table layout");
+    cudaError_t e = cudaMemcpyAsync(table, pl->rows.data(), (size_t)nrows * sizeof(int4), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    int kh, kw;
+    kernel_dims(kind, kh, kw);
+    hconv_pack_kernel<<<(nrows * 64 + 255) / 256, 256, 0, s>>>(w, table, nrows, Cout, Cin, kh, kw, pl->transposed,
+                                                               reinterpret_cast<__nv_bfloat16 *>(packed));
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}
+
+// in: bf16 NHWC (B, H, W, Cin).  out: bf16 NHWC (out_f32 = 0) / fp32 NHWC (out_f32 = 1) / fp32 NCHW (VQB_CONVT_K4S2_OUT).
+extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *bias, void *out, int B, int Cin, int H, int W,
+                               int Cout, int kind, int relu, int out_f32, void *stream) {
+    if (!in || !packed || !out) return VQB_ERR_BAD_ARG;
+    if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0) return VQB_ERR_BAD_ARG;
+    const Plan *pl = get_plan(kind, Cin, Cout);
+    if (!pl) return VQB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(packed)) & 15) return VQB_ERR_ALIGNMENT;
+    if (pl->s2d && ((H | W) & 1)) return VQB_ERR_UNSUPPORTED;
+    if (kind == VQB_CONVT_K4S2_OUT) out_f32 = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    HParams q;
+    memset(&q, 0, sizeof(q));
+    q.bias = bias; q.out = out;
+    // the GEMM's pixel grid: the input grid, or the space-to-depth grid of a stride-2 conv
+    const int GH = pl->s2d ? H / 2 : H, GW = pl->s2d ? W / 2 : W;
+    q.B = B; q.H = GH; q.W = GW;
+    q.MT = (GW > 8 && 2 * pl->NCOL <= 256) ? 2 : 1;
+    q.TW = 8 * q.MT;
+    q.BH = pow2_ceil_h(GH) < 16 ? pow2_ceil_h(GH) : 16;
+    q.BN = 16 / q.BH;
+    q.halo = pl->halo;
+    q.WP = q.TW + 2 * q.halo;
+    q.tiles_x = (GW + q.TW - 1) / q.TW;
+    q.tiles_y = (GH + q.BH - 1) / q.BH;
+    q.tiles_n = (B + q.BN - 1) / q.BN;
+    q.npass = pl->npass;
+    q.ntiles = (long long)q.tiles_x * q.tiles_y * q.tiles_n * q.npass;
+    q.NCOL = pl->NCOL;
+    q.nchunks = pl->nchunks;
+    for (int k = 0; k < pl->nchunks; ++k) { q.chunk_c0[k] = pl->chunk_c0[k]; q.chunk_p[k] = pl->chunk_p[k]; }
+    int total_steps = 0;
+    for (int ps = 0; ps < pl->npass; ++ps) {
+        q.nsteps[ps] = pl->nsteps[ps];
+        total_steps += pl->nsteps[ps];
+        for (int i = 0; i < pl->nsteps[ps]; ++i) {
+            const PlanStep &a = pl->steps[ps][i];
+            HStep &d = q.steps[ps][i];
+            d.a_off16 = (uint32_t)((((a.dy + q.halo) * q.BN) * q.WP + (a.dx + q.halo)) * 8);
+            d.w_row = (uint16_t)a.w_row; d.nb8 = (uint8_t)(a.nb / 8); d.d_col = (uint8_t)a.d_col; d.flags = (uint8_t)a.flags;
+        }
+    }
+    q.halo_bytes = (q.BH + 2 * q.halo) * q.BN * q.WP * 128;
+    q.halo_stride = (q.halo_bytes + 1023) & ~1023;
+    q.wst_bytes = pl->nbmax * 128;
+    q.nhb = pl->nchunks == 1 ? 2 : HC_MAX_HB;
+    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4) + 16 + 256 * 4 + 1024;
+    int S = (227 * 1024 - q.nhb * q.halo_stride - MISC) / q.wst_bytes;
+    if (S > HC_MAX_STAGES) S = HC_MAX_STAGES;
+    if (S < 2) return VQB_ERR_UNSUPPORTED;
+    q.resident = total_steps <= S ? 1 : 0;
+    if (q.resident) S = total_steps;
+    else if (S > 12) S = 12;
+    q.S = S;
+    q.epi_mode = pl->epi_mode; q.cg = pl->cg; q.sy = pl->sy; q.sx = pl->sx;
+    q.OH = GH * pl->sy; q.OW = GW * pl->sx;
+    if (pl->epi_mode == EPI_SHUFFLE_NCHW) { q.OH = 2 * GH; q.OW = 2 * GW; }
+    q.Cout = Cout; q.relu = relu; q.out_f32 = out_f32;
+    q.bias_mod = Cout;
+
+    CUtensorMap tin, tw, twh;
+    {
+        // 5-D view (c, x, n, p, y); p is the row parity of the space-to-depth view (size 1 otherwise)
+        typedef unsigned long long u64;
+        u64 dims[5], strides[4];
+        if (pl->s2d) {
+            dims[0] = 2ull * Cin; dims[1] = (u64)GW; dims[2] = (u64)B; dims[3] = 2; dims[4] = (u64)GH;
+            strides[0] = 2ull * Cin * 2; strides[1] = (u64)H * W * Cin * 2; strides[2] = (u64)W * Cin * 2; strides[3] = 2ull * W * Cin * 2;
+        } else {
+            dims[0] = (u64)Cin; dims[1] = (u64)W; dims[2] = (u64)B; dims[3] = 1; dims[4] = (u64)H;
+            strides[0] = (u64)Cin * 2; strides[1] = (u64)H * W * Cin * 2; strides[2] = (u64)H * W * Cin * 2; strides[3] = (u64)W * Cin * 2;
+        }
+        const uint32_t box[5] = {64u, (uint32_t)q.WP, (uint32_t)q.BN, 1u, (uint32_t)(q.BH + 2 * q.halo)};
+        int rc = vqb_encode_tmap_nd(&tin, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, in, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        const int nrows = (int)pl->rows.size();
+        rc = vqb_encode_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, packed, 64, (uint64_t)nrows, 128, 64, (uint32_t)pl->nbmax,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = vqb_encode_tmap_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, packed, 64, (uint64_t)nrows, 128, 64,
+                                (uint32_t)(pl->nbhalf ? pl->nbhalf : pl->nbmax), CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const int smem = q.nhb * q.halo_stride + q.S * q.wst_bytes + MISC;
+    static int attr_max = 0;
+    if (smem > attr_max) {
+        cudaError_t e = cudaFuncSetAttribute(hconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_max = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
+    if (cudaError_t le = vqb_launch(hconv_kernel, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)) return (int)le;
+    VQB_COUNT_LAUNCH(1);
+    return vqb_cuda_status(cudaGetLastError());
+}

@@ -224,3 +224,6 @@ int vqb_encode_tmap_2d(CUtensorMap *map, CUtensorMapDataType dtype, const void *
 int vqb_encode_tmap_4d(CUtensorMap *map, CUtensorMapDataType dtype, const void *base, const uint64_t dims[4],
                        const uint64_t strides_bytes[3], const uint32_t box[4], const uint32_t elem_strides[4],
                        CUtensorMapSwizzle swizzle);
+int vqb_encode_tmap_nd(CUtensorMap *map, CUtensorMapDataType dtype, const void *base, int rank,
+                       const unsigned long long *dims, const unsigned long long *strides_bytes, const uint32_t *box,
+                       CUtensorMapSwizzle swizzle);

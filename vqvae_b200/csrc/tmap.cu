@@ -45,3 +45,19 @@ int vqb_encode_tmap_4d(CUtensorMap *map, CUtensorMapDataType dtype, const void *
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : VQB_ERR_BAD_ARG;
 }
+
+// rank-`rank` (<= 5) tiled map, element strides 1 (the bf16 kernels' 5-D activation views)
+int vqb_encode_tmap_nd(CUtensorMap *map, CUtensorMapDataType dtype, const void *base, int rank,
+                       const unsigned long long *dims, const unsigned long long *strides_bytes, const uint32_t *box,
+                       CUtensorMapSwizzle swizzle) {
+    auto enc = get_encode();
+    if (!enc) return VQB_ERR_NO_DEVICE;
+    if (rank < 1 || rank > 5) return VQB_ERR_BAD_ARG;
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void *>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : VQB_ERR_BAD_ARG;
+}

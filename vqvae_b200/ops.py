@@ -98,6 +98,70 @@ def conv2d(x, w_packed, bias, *, B, Cin, H, W, Cout, kh, kw, stride, pad, transp
     return out
 
 
+def conv_kind(kh, stride, transposed, cout):
+    """enum vqb_conv_kind of a layer of the hot path, or None when the bf16 kernels do not cover it."""
+    if not transposed:
+        return {(1, 1): _lib.CONV_K1, (3, 1): _lib.CONV_K3, (4, 2): _lib.CONV_K4S2}.get((kh, stride))
+    if (kh, stride) == (3, 1):
+        return _lib.CONVT_K3
+    if (kh, stride) == (4, 2):
+        return _lib.CONVT_K4S2_OUT if cout <= 4 else _lib.CONVT_K4S2
+    return None
+
+
+def pack_conv_weight_bf16(w, kind, out=None):
+    """fp32 conv / conv-transpose weight -> the bf16 k-step-ordered packing of vqb_pack_conv_weight_bf16
+    (None when the shape is not covered).  `out`: repack into an existing buffer (same shape) in place."""
+    _require_cuda(w, "weight")
+    w = _f32c(w.detach())
+    transposed = kind in (_lib.CONVT_K3, _lib.CONVT_K4S2, _lib.CONVT_K4S2_OUT)
+    cin, cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+    nbytes = lib().vqb_conv_bf16_packed_bytes(kind, cout, cin)
+    if nbytes == 0:
+        return None
+    if out is None:
+        # (torch's caching allocator hands out 512-byte aligned blocks: the 128-byte alignment the TMA maps need)
+        out = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    check(lib().vqb_pack_conv_weight_bf16(w.data_ptr(), out.data_ptr(), kind, cout, cin, _stream()), "pack_conv_weight_bf16")
+    return out
+
+
+def conv2d_bf16(x, packed, bias, *, B, Cin, H, W, Cout, kind, relu=False, out_f32=False):
+    """One layer on bf16 NHWC input through vqb_conv2d_bf16; returns bf16 NHWC, fp32 NHWC (out_f32) or, for
+    CONVT_K4S2_OUT, the fp32 NCHW module output."""
+    _require_cuda(x, "input")
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise RuntimeError("conv2d_bf16: input must be a contiguous bf16 NHWC tensor")
+    if kind == _lib.CONV_K4S2:
+        shape, dt = (B, H // 2, W // 2, Cout), (torch.float32 if out_f32 else torch.bfloat16)
+    elif kind == _lib.CONVT_K4S2:
+        shape, dt = (B, 2 * H, 2 * W, Cout), (torch.float32 if out_f32 else torch.bfloat16)
+    elif kind == _lib.CONVT_K4S2_OUT:
+        shape, dt = (B, Cout, 2 * H, 2 * W), torch.float32
+    else:
+        shape, dt = (B, H, W, Cout), (torch.float32 if out_f32 else torch.bfloat16)
+    out = torch.empty(shape, dtype=dt, device=x.device)
+    span = _Span(f"bf16 kind{kind} {Cin}->{Cout} {H}x{W}")
+    check(lib().vqb_conv2d_bf16(x.data_ptr(), packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                out.data_ptr(), B, Cin, H, W, Cout, kind, int(bool(relu)), int(bool(out_f32)),
+                                _stream()), "conv2d_bf16")
+    span.done()
+    return out
+
+
+def residual_layer_bf16(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, relu_out):
+    """out = act(r + W2.relu(W1 (*) r)) on bf16 NHWC buffers, one persistent tcgen05 kernel (vqb_residual_layer_bf16)."""
+    _require_cuda(r, "input")
+    if r.dtype != torch.bfloat16 or not r.is_contiguous():
+        raise RuntimeError("residual_layer_bf16: input must be a contiguous bf16 NHWC tensor")
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=r.device)
+    span = _Span(f"bf16 res {C}->{Cmid}->{C} {H}x{W}")
+    check(lib().vqb_residual_layer_bf16(r.data_ptr(), w1_packed.data_ptr(), w2_packed.data_ptr(), out.data_ptr(),
+                                        B, H, W, C, Cmid, int(bool(relu_out)), _stream()), "residual_layer_bf16")
+    span.done()
+    return out
+
+
 def residual_layer(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, relu_out, precision=FP32):
     """out = act(r + W2.relu(W1 (*) r)) on NHWC buffers (vqb_residual_layer_f32)."""
     _require_cuda(r, "input")
