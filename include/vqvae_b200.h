@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VQB_ABI_VERSION 1
+#define VQB_ABI_VERSION 2
 
 enum vqb_status {
     VQB_OK = 0,
@@ -49,14 +49,19 @@ enum vqb_status {
 
 enum vqb_layout { VQB_NCHW = 0, VQB_NHWC = 1 };
 
-/* arithmetic of a convolution entry point */
+/* arithmetic of a convolution entry point that takes fp32 activations (vqb_conv2d_f32,
+ * vqb_residual_*_f32).  VQB_BF16 names the bf16-operand pipeline, whose activations are bf16:
+ * the *_f32 entry points answer VQB_ERR_UNSUPPORTED to it -- use vqb_conv2d_bf16 & co.   */
 enum vqb_precision {
     VQB_FP32 = 0,  /* fp32 FFMA accumulate (CUDA cores): the reference's CPU numerics   */
     VQB_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (cuDNN's default)     */
-    VQB_BF16 = 2   /* tcgen05 kind::f16 on bf16 operands, fp32 accumulate in TMEM       */
+    VQB_BF16 = 2   /* tcgen05 kind::f16 on bf16 operands and activations (bf16 entry points only) */
 };
 
 int vqb_abi_version(void);
+/* 0: release library -- never reads the environment, no diagnostic / work-skipping code paths
+ * compiled in.  1: built with -DVQB_DIAG=1 (tools/diag experiments only).                  */
+int vqb_diag_build(void);
 const char *vqb_error_string(int code);
 /* SM count and compute capability of the current device. */
 int vqb_device_info(int *sm_count, int *cc_major, int *cc_minor);
@@ -117,6 +122,16 @@ int vqb_pack_conv_weight_bf16(const float *w, void *packed, int kind, int Cout, 
 int vqb_conv2d_bf16(const void *in, const void *packed, const float *bias, void *out, int B,
                     int Cin, int H, int W, int Cout, int kind, int relu, int out_f32,
                     void *stream);
+
+/* encoder.py:29-31 for the bf16 pipeline: fp32 NCHW image (B,3,H,W) -> bf16 NHWC (B,H/2,W/2,Cout),
+ * Cout == 64; w_packed from vqb_pack_conv_weight_f32.                                       */
+int vqb_conv_in_bf16(const float *x, const float *w_packed, const float *bias, void *out, int B,
+                     int H, int W, int Cout, int relu, void *stream);
+/* VectorQuantizer core for the bf16 pipeline: as vqb_vq_forward_deferred_f32 (fp32 z, bit-exact
+ * idx, deferred SSE) but zq is written as bf16 rows (N, D); D == 64 only.                    */
+int vqb_vq_forward_bf16zq_f32(const float *z, const float *codebook, int64_t N, int K, int D,
+                              int64_t *idx, void *zq_bf16, double *sse, int32_t *hist,
+                              void *workspace, size_t workspace_bytes, void *stream);
 
 /* One ResidualLayer application on bf16 NHWC activations (residual.py:18-29 as evaluated,
  * SURVEY Q2):  out = act( r + W2 . relu( W1 (*) r ) ),  act = ReLU iff relu_out.

@@ -25,7 +25,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vqvae_b200.h but not exported"
     lib.vqb_abi_version.restype = ctypes.c_int
-    assert lib.vqb_abi_version() == 1
+    assert lib.vqb_abi_version() == 2
+    assert lib.vqb_diag_build() == 0          # the shipped library never reads the environment
     lib.vqb_error_string.restype = ctypes.c_char_p
     assert b"workspace" in lib.vqb_error_string(-3)
 

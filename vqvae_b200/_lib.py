@@ -23,6 +23,7 @@ _vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
 # name -> (restype, argtypes); mirrors the header one to one (tests check this)
 SIGNATURES = {
     "vqb_abi_version": (_i, []),
+    "vqb_diag_build": (_i, []),
     "vqb_error_string": (C.c_char_p, [_i]),
     "vqb_device_info": (_i, [C.POINTER(_i)] * 3),
     "vqb_pack_conv_weight_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -48,6 +49,8 @@ SIGNATURES = {
     "vqb_conv_bf16_packed_bytes": (_sz, [_i, _i, _i]),
     "vqb_pack_conv_weight_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "vqb_conv2d_bf16": (_i, [_vp, _vp, _vp, _vp] + [_i] * 8 + [_vp]),
+    "vqb_conv_in_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "vqb_vq_forward_bf16zq_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vqb_residual_layer_bf16": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "vqb_debug_vq_scores_f32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
 }
@@ -63,7 +66,7 @@ def lib():
             fn = getattr(handle, name)   # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.vqb_abi_version() != 1:
+        if handle.vqb_abi_version() != 2:
             raise RuntimeError("libvqvae_b200.so ABI version mismatch")
         _lib = handle
     return _lib

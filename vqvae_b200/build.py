@@ -35,6 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
                "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c", src, "-o", obj]
+        if os.environ.get("VQB_DIAG") == "1":        # diagnostic build: env knobs + in-kernel timelines (tools/diag)
+            cmd.insert(1, "-DVQB_DIAG=1")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

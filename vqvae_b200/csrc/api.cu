@@ -11,8 +11,10 @@ size_t vq_tc_workspace_bytes(int K);
 bool vq_tc_supported(long long N, int K, int D);
 size_t vq_ws_marker_offset(int K);
 int launch_vq_reduce_sse(const void *ws, int K, double *sse, cudaStream_t s);
-int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
-                 int *hist, void *ws, float *dbg, int defer, cudaStream_t s);
+int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, void *zq, double *sse,
+                 int *hist, void *ws, float *dbg, int defer, int zq_bf16, cudaStream_t s);
+int launch_conv_in_tc_ex(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int Cout,
+                         int relu, int out_bf16, cudaStream_t s);
 
 int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
                         int Cout, int relu, cudaStream_t s);
@@ -33,14 +35,14 @@ bool conv_tc_supported(const ConvLaunch &p);
 int launch_conv_tc(const ConvLaunch *ph, int nph, const float *w_tc, int total_taps, cudaStream_t s);
 
 int vqb_halo_wp() {
-    static const int wp = [] { const char *e = getenv("VQB_HALO_WP"); return (e && atoi(e) == 16) ? 16 : 10; }();
+    static const int wp = [] { const char *e = vqb_getenv("VQB_HALO_WP"); return (e && atoi(e) == 16) ? 16 : 10; }();
     return wp;
 }
 
 int vqb_pdl_enabled() {
     static int on = -1;
     if (on < 0) {
-        const char *e = getenv("VQB_PDL");
+        const char *e = vqb_getenv("VQB_PDL");
         on = e ? (atoi(e) != 0) : 1;
     }
     return on;
@@ -56,6 +58,9 @@ extern "C" int vqb_set_vq_kernel(int which) {
 extern "C" unsigned long long vqb_launch_count(void) { return g_vqb_launches; }
 
 extern "C" int vqb_abi_version(void) { return VQB_ABI_VERSION; }
+
+// 0 = release library (never reads the environment, no work-skipping paths compiled in); 1 = diagnostic build
+extern "C" int vqb_diag_build(void) { return VQB_DIAG; }
 
 extern "C" const char *vqb_error_string(int code) {
     switch (code) {
@@ -101,6 +106,7 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
     if ((in_layout != VQB_NCHW && in_layout != VQB_NHWC) || (out_layout != VQB_NCHW && out_layout != VQB_NHWC))
         return VQB_ERR_BAD_ARG;
     if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
+    if (precision == VQB_BF16) return VQB_ERR_UNSUPPORTED;      // bf16 operands need bf16 activations: vqb_conv2d_bf16
     if (skip && out_layout != VQB_NHWC) return VQB_ERR_BAD_ARG;
     if (kh * kw > VQB_MAX_TAPS) return VQB_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
@@ -112,14 +118,18 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
     // the two HBM-bound end layers have dedicated kernels (conv_edge.cu)
     if (kh == 4 && kw == 4 && stride == 2 && pad == 1 && !skip) {
         if (!transposed && precision != VQB_FP32 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
-            conv_in_tc_supported(Cin, Cout, H, W, out))       // tcgen05 with a hand-built im2col tile
-            return launch_conv_in_tc(in, w_packed, bias, out, B, H, W, Cout, relu, s);
+            conv_in_tc_supported(Cin, Cout, H, W, out)) {     // tcgen05 with a hand-built im2col tile
+            const int rc = launch_conv_in_tc(in, w_packed, bias, out, B, H, W, Cout, relu, s);
+            if (rc != VQB_ERR_UNSUPPORTED) return rc;
+        }
         if (!transposed && Cin == 3 && Cout % 32 == 0 && in_layout == VQB_NCHW && out_layout == VQB_NHWC &&
             H % 2 == 0 && W % 2 == 0 && (size_t)16 * Cin * Cout * 4 <= 48 * 1024)
             return launch_conv_in_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
         if (transposed && precision != VQB_FP32 && in_layout == VQB_NHWC && out_layout == VQB_NCHW &&
-            convt_shuffle_supported(Cin, Cout, in, out))      // tcgen05: one 3x3-neighbourhood GEMM + pixel shuffle
-            return launch_convt_shuffle(in, w_packed + (size_t)2 * 16 * Cin * Cout, bias, out, B, Cin, H, W, Cout, relu, s);
+            convt_shuffle_supported(Cin, Cout, in, out)) {    // tcgen05: one 3x3-neighbourhood GEMM + pixel shuffle
+            const int rc = launch_convt_shuffle(in, w_packed + (size_t)2 * 16 * Cin * Cout, bias, out, B, Cin, H, W, Cout, relu, s);
+            if (rc != VQB_ERR_UNSUPPORTED) return rc;
+        }
         if (transposed && Cout == 3 && Cin % 4 == 0 && Cin <= 128 && ((Cin / 4) & (Cin / 4 - 1)) == 0 &&
             in_layout == VQB_NHWC && out_layout == VQB_NCHW)
             return launch_convt_out_k4s2(in, w_packed, bias, out, B, Cin, H, W, Cout, relu, s);
@@ -146,8 +156,16 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
                 p.tap_dy[t] = transposed ? pad - r : r - pad;
                 p.tap_dx[t] = transposed ? pad - c : c - pad;
             }
-        if (want_tc && conv_halo_supported(p)) return launch_conv_halo(p, w_tc, s);
-        if (want_tc && conv_tc_supported(p)) return launch_conv_tc(&p, 1, w_tc, kh * kw, s);
+        // a tensor-core launcher that cannot fit the shape (shared memory, ring depth) answers VQB_ERR_UNSUPPORTED
+        // before launching anything: fall through to the next kernel that can run it
+        if (want_tc && conv_halo_supported(p)) {
+            const int rc = launch_conv_halo(p, w_tc, s);
+            if (rc != VQB_ERR_UNSUPPORTED) return rc;
+        }
+        if (want_tc && conv_tc_supported(p)) {
+            const int rc = launch_conv_tc(&p, 1, w_tc, kh * kw, s);
+            if (rc != VQB_ERR_UNSUPPORTED) return rc;
+        }
         return small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
     }
     // stride-s transposed conv: s*s sub-pixel phases, each a stride-1 gather conv
@@ -183,7 +201,14 @@ extern "C" int vqb_conv2d_f32(const float *in, const float *w_packed, const floa
             rc = small ? launch_conv_small_cout(p, s) : launch_conv_ffma(p, s);
             if (rc != 0) return rc;
         }
-    if (tc_multi && nph > 0) return launch_conv_tc(phases, nph, w_tc, kh * kw, s);   // one launch, blockIdx.y = phase
+    if (tc_multi && nph > 0) {
+        const int rc = launch_conv_tc(phases, nph, w_tc, kh * kw, s);   // one launch, blockIdx.y = phase
+        if (rc != VQB_ERR_UNSUPPORTED) return rc;
+        for (int i = 0; i < nph; ++i) {                                 // did not fit: the phases one by one on CUDA cores
+            const int rc2 = small ? launch_conv_small_cout(phases[i], s) : launch_conv_ffma(phases[i], s);
+            if (rc2 != 0) return rc2;
+        }
+    }
     return 0;
 }
 
@@ -234,7 +259,7 @@ static int vq_forward_impl(const float *z, const float *codebook, int64_t N, int
     if (g_vq_kernel == 2 && !tc_ok) return VQB_ERR_UNSUPPORTED;
     if (tc_ok && g_vq_kernel != 1)
         return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
-                            nullptr, defer, (cudaStream_t)stream);
+                            nullptr, defer, 0, (cudaStream_t)stream);
     const int rc = launch_vq_exact(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
                                    (cudaStream_t)stream);
     if (rc || !defer) return rc;
@@ -243,13 +268,39 @@ static int vq_forward_impl(const float *z, const float *codebook, int64_t N, int
                                            (cudaStream_t)stream));
 }
 
+// VQB_BF16 pipeline: same contract as vqb_vq_forward_deferred_f32 (fp32 z in, bit-exact idx) but z_q leaves as bf16
+// rows for the decoder's first conv; tcgen05 kernel only (D == 64).
+extern "C" int vqb_vq_forward_bf16zq_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
+                                         void *zq_bf16, double *sse, int32_t *hist, void *workspace,
+                                         size_t workspace_bytes, void *stream) {
+    if (!z || !codebook || !idx || !zq_bf16 || !sse || !hist || !workspace) return VQB_ERR_BAD_ARG;
+    if (N <= 0 || K <= 0 || D <= 0) return VQB_ERR_BAD_ARG;
+    if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(codebook) |
+                         reinterpret_cast<uintptr_t>(zq_bf16) | reinterpret_cast<uintptr_t>(workspace);
+    if (al & 15) return VQB_ERR_ALIGNMENT;
+    if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
+    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq_bf16, sse, hist, workspace, nullptr, 1, 1,
+                        (cudaStream_t)stream);
+}
+
+// encoder.py:29-31 in the VQB_BF16 pipeline: fp32 NCHW image in, bf16 NHWC activation out (Cout == 64); the 48-tap
+// contraction itself runs as kind::tf32 on the fp32 pixels.  w_packed: vqb_pack_conv_weight_f32 of the layer.
+extern "C" int vqb_conv_in_bf16(const float *x, const float *w_packed, const float *bias, void *out, int B, int H, int W,
+                                int Cout, int relu, void *stream) {
+    if (!x || !w_packed || !out) return VQB_ERR_BAD_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return VQB_ERR_BAD_ARG;
+    if (!conv_in_tc_supported(3, Cout, H, W, out) || Cout != 64) return VQB_ERR_UNSUPPORTED;
+    return launch_conv_in_tc_ex(x, w_packed, bias, out, B, H, W, Cout, relu, 1, (cudaStream_t)stream);
+}
+
 extern "C" int vqb_debug_vq_scores_f32(const float *z, const float *codebook, int64_t N, int K, int D, int64_t *idx,
                                        float *zq, double *sse, int32_t *hist, void *workspace,
                                        size_t workspace_bytes, float *scores, void *stream) {
     if (!z || !codebook || !idx || !zq || !sse || !hist || !workspace || !scores) return VQB_ERR_BAD_ARG;
     if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
     if (workspace_bytes < vqb_vq_workspace_bytes(N, K, D)) return VQB_ERR_WORKSPACE;
-    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores, 0,
+    return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, scores, 0, 0,
                         (cudaStream_t)stream);
 }
 
@@ -259,9 +310,12 @@ extern "C" int vqb_residual_layer_f32(const float *r, const float *w1_packed, co
     if (!r || !w1_packed || !w2_packed || !out || !tmp) return VQB_ERR_BAD_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cmid <= 0) return VQB_ERR_BAD_ARG;
     if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
-    if (precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out))
-        return launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C, Cmid,
-                             relu_out, 1, (cudaStream_t)stream);
+    if (precision == VQB_BF16) return VQB_ERR_UNSUPPORTED;      // see vqb_residual_layer_bf16
+    if (precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out)) {
+        const int rc = launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C, Cmid,
+                                     relu_out, 1, (cudaStream_t)stream);
+        if (rc != VQB_ERR_UNSUPPORTED) return rc;               // (e.g. C = 256, Cmid = 128: shared memory) -> generic path
+    }
     // two launches through the generic path (residual.py:20-24 then :23-24,:28)
     int rc = vqb_conv2d_f32(r, w1_packed, nullptr, nullptr, tmp, B, C, H, W, Cmid, 3, 3, 1, 1, 0, VQB_NHWC, VQB_NHWC, 1,
                             precision, stream);
@@ -277,7 +331,8 @@ extern "C" int vqb_residual_stack_f32(const float *r, const float *w1_packed, co
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cmid <= 0 || n_layers < 1) return VQB_ERR_BAD_ARG;
     if (n_layers > 1 && !scratch) return VQB_ERR_BAD_ARG;
     if (precision < VQB_FP32 || precision > VQB_BF16) return VQB_ERR_BAD_ARG;
-    static const bool fuse = [] { const char *e = getenv("VQB_RES_FUSE"); return !(e && e[0] == '0'); }();
+    if (precision == VQB_BF16) return VQB_ERR_UNSUPPORTED;
+    static const bool fuse = [] { const char *e = vqb_getenv("VQB_RES_FUSE"); return !(e && e[0] == '0'); }();
     if (fuse && n_layers > 1 && precision != VQB_FP32 && res_tc_supported(C, Cmid, r, out)) {
         // all applications in ONE launch: the activation never leaves shared memory between them
         const int rc = launch_res_tc(r, w1_packed + (size_t)9 * C * Cmid, w2_packed + (size_t)C * Cmid, out, B, H, W, C,
@@ -313,7 +368,7 @@ extern "C" int vqb_memcpy_async(void *dst, const void *src, size_t bytes, int ki
             p = nullptr;
         return reinterpret_cast<PFN_cuMemcpyAsync>(p);
     }();
-    static const bool use_rt = [] { const char *e = getenv("VQB_MEMCPY_RUNTIME"); return e && e[0] == '1'; }();
+    static const bool use_rt = [] { const char *e = vqb_getenv("VQB_MEMCPY_RUNTIME"); return e && e[0] == '1'; }();
     if (fn && !use_rt) {
         const int rc = fn((unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, bytes, stream);
         return rc == 0 ? 0 : VQB_ERR_BAD_ARG;

@@ -7,6 +7,16 @@
 
 #define VQB_MAX_TAPS 16
 
+// Experiment / diagnostic knobs (VQB_* environment variables, the work-skipping VQB_TC_FLAGS bits, in-kernel
+// timelines) exist only in a library built with -DVQB_DIAG=1 (VQB_DIAG=1 python -m vqvae_b200.build, used by
+// tools/diag).  The release library never reads the environment: vqb_getenv() is a constant nullptr there and the
+// flag tests in the kernels fold away.
+#ifndef VQB_DIAG
+#define VQB_DIAG 0
+#endif
+#include <stdlib.h>
+static inline const char *vqb_getenv(const char *name) { return VQB_DIAG ? getenv(name) : nullptr; }
+
 // One launch of the generalised gather-form convolution
 //   out[n, gy*out_step+out_py, gx*out_step+out_px, co] =
 //       act( bias[co] + skip + sum_{t<ntaps, ci} in[n, gy*in_step+dy[t], gx*in_step+dx[t], ci]

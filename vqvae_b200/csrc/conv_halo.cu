@@ -284,7 +284,7 @@ int ch_pow2_ceil(int x) {
 int conv_halo_mode() {          // on by default; VQB_CONV_HALO=0 falls back to the per-tap TMA kernel (conv_tc.cu)
     static int mode = -1;
     if (mode < 0) {
-        const char *e = getenv("VQB_CONV_HALO");
+        const char *e = vqb_getenv("VQB_CONV_HALO");
         mode = e ? atoi(e) : 1;
     }
     return mode;
@@ -314,7 +314,7 @@ int launch_conv_halo_ex(const ConvLaunch &p, const float *w_tc, int shuffle_cout
     q.tiles_y = (p.H + q.BH - 1) / q.BH;
     const int tiles_n = (p.B + q.BN - 1) / q.BN;
     {
-        static const int want = [] { const char *e = getenv("VQB_CONV_NMMA"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        static const int want = [] { const char *e = vqb_getenv("VQB_CONV_NMMA"); return (e && atoi(e) == 1) ? 1 : 2; }();
         q.nmma = (want == 2 && 2 * p.Cout <= 256) ? 2 : 1;       // <= 256 TMEM columns: two CTAs per SM can still allocate
     }
     q.shuffle_cout = shuffle_cout;

@@ -13,6 +13,8 @@
 // The first version gathered straight from global memory with per-tap index arithmetic: 1480
 // instructions per thread, issue-bound at 20 us for cfg2 (profiles/r01_step_kernels_ncu.txt).
 // Shapes outside the fast path (OW not dividing 128, tiles straddling images) keep that gather.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -28,6 +30,7 @@ struct ConvInParams {
     int log2_ow;    // fast path
     int raw_floats; // fast path: 3 * (2R+2) * (W+2)
     int tma_store;  // epilogue through shared memory + TMA (Cout == 64)
+    int out_bf16;   // VQB_BF16 mode: the NHWC output is bf16 (the 128 x 64 tile is one 16 KB swizzled atom); needs tma_store
 };
 
 template <int COUT>
@@ -173,7 +176,24 @@ conv_in_tc_kernel(const __grid_constant__ CUtensorMap tma_out, const ConvInParam
             float v[32];
             ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             ptx::tmem_ld_wait32(v);
-            if (p.tma_store) {
+            if (p.tma_store && p.out_bf16) {
+                // bf16 output: 64 channels = one 128-byte row; this thread's 32 columns are four 16-byte pieces
+                unsigned char *orow = sm + row * 128;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        o[u] = v[i + u] + bias_s[c0 + i + u];
+                        if (p.relu) o[u] = fmaxf(o[u], 0.f);
+                    }
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+                    *reinterpret_cast<uint4 *>(orow + ((((c0 + i) >> 3) ^ (row & 7)) << 4)) =
+                        make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                                   *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+                }
+            } else if (p.tma_store) {
                 // the A operand is dead (all MMAs completed): 128 x Cout tile, one 16 KB swizzled atom per 32 channels
                 unsigned char *orow = sm + (c0 >> 5) * 16384 + row * 128;
 #pragma unroll
@@ -199,9 +219,9 @@ conv_in_tc_kernel(const __grid_constant__ CUtensorMap tma_out, const ConvInParam
     ptx::tc_fence_before();
     __syncthreads();
     if (p.tma_store && tid == 0) {
-        // box {32 channels, 128 pixels}; rows past the last pixel are clipped by the tensor map
-#pragma unroll
-        for (int a = 0; a < Cout / 32; ++a)
+        // box {32 channels, 128 pixels} ({64, 128} for bf16); rows past the last pixel are clipped by the tensor map
+        const int natoms = p.out_bf16 ? 1 : Cout / 32;
+        for (int a = 0; a < natoms; ++a)
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
                              "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + a * 16384), "r"(a * 32),
                              "r"((int)pix0) : "memory");
@@ -219,14 +239,23 @@ bool conv_in_tc_supported(int Cin, int Cout, int H, int W, const void *y) {
 }
 
 // wp = FFMA packing [(r*4+s)*3 + c][co] (first region of vqb_pack_conv_weight_f32)
+int launch_conv_in_tc_ex(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int Cout,
+                         int relu, int out_bf16, cudaStream_t s);
 int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float *y, int B, int H, int W, int Cout,
                       int relu, cudaStream_t s) {
+    return launch_conv_in_tc_ex(x, wp, bias, y, B, H, W, Cout, relu, 0, s);
+}
+
+int launch_conv_in_tc_ex(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int Cout,
+                         int relu, int out_bf16, cudaStream_t s) {
     const int OH = H / 2, OW = W / 2;
     const long long npix = (long long)B * OH * OW;
     const long long blocks = (npix + 127) / 128;
     if (blocks <= 0 || blocks > 0x7fffffffLL || npix > 0x7fffffffLL) return VQB_ERR_UNSUPPORTED;
     ConvInParams q;
-    q.x = x; q.wp = wp; q.bias = bias; q.y = y; q.B = B; q.H = H; q.W = W; q.relu = relu;
+    if (out_bf16 && Cout != 64) return VQB_ERR_UNSUPPORTED;
+    q.x = x; q.wp = wp; q.bias = bias; q.y = reinterpret_cast<float *>(y); q.B = B; q.H = H; q.W = W; q.relu = relu;
+    q.out_bf16 = out_bf16;
     q.R = 0; q.log2_ow = 0; q.raw_floats = 0;
     // fast path: whole output rows per tile, tiles inside one image, 16-byte aligned input rows
     if (OW >= 2 && OW <= 128 && (OW & (OW - 1)) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
@@ -239,8 +268,11 @@ int launch_conv_in_tc(const float *x, const float *wp, const float *bias, float 
     }
     q.tma_store = Cout == 64 ? 1 : 0;        // (Cout 128 would need 64 KB of staging: direct stores)
     CUtensorMap tout;
-    int rc = vqb_encode_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, y, (uint64_t)Cout, (uint64_t)npix,
-                                (uint64_t)Cout * 4, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = out_bf16
+        ? vqb_encode_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y, (uint64_t)Cout, (uint64_t)npix,
+                             (uint64_t)Cout * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B)
+        : vqb_encode_tmap_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, y, (uint64_t)Cout, (uint64_t)npix,
+                             (uint64_t)Cout * 4, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const int smem = 2 * 16384 + 2 * Cout * 128 + 16 + Cout * 4 + q.raw_floats * 4 + 16 + 1024;
     if (smem > 200 * 1024) return VQB_ERR_UNSUPPORTED;

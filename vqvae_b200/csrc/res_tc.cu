@@ -462,7 +462,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     ResTcParams q;
     q.napp = napp;
     {
-        static const int want = [] { const char *e = getenv("VQB_RES_NMMA"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
+        static const int want = [] { const char *e = vqb_getenv("VQB_RES_NMMA"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
         q.nmma = want;
         while (q.nmma > 1 && q.nmma * Cmid + C > 512) q.nmma >>= 1;      // TMEM columns: nmma D1 partials + D2
         // the k-steps of every application must deal out the same way (fused == separate launches, bit for bit)
@@ -535,7 +535,7 @@ int launch_res_tc(const float *r, const float *w1_tc, const float *w2_tc, float 
     }
     q.stages = stages;
     {
-        static const int want = [] { const char *e = getenv("VQB_RES_NPROD"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        static const int want = [] { const char *e = vqb_getenv("VQB_RES_NPROD"); return (e && atoi(e) == 1) ? 1 : 2; }();
         q.nprod = (q.staged && stages % 2 == 0) ? want : 1;
     }
     const int smem = stages * stage_bytes + fixed;

@@ -30,6 +30,8 @@
 // and a shared-memory code histogram.
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -96,6 +98,7 @@ struct VqTcParams {
     int *hist;
     float *dbg;            // optional (N, nchunks*256) raw approximate scores
     int flags;             // perf-experiment knobs (env VQB_TC_FLAGS), 0 in production
+    int zq_bf16;           // VQB_BF16 pipeline: z_q leaves as bf16 rows (the decoder's first conv reads bf16)
 };
 
 __device__ __forceinline__ bool vq_better(float dn, int kn, float db, int kb) {
@@ -136,15 +139,16 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     unsigned char *sm = smem_raw + (sbase - raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kflags = VQB_DIAG ? p.flags : 0;          // release build: every diagnostic branch folds away
     auto kmark = [&](int i) {          // kernel-level timeline of CTA 0 (slots 32..), VQB_TC_FLAGS & 8
-        if ((p.flags & 8) && blockIdx.x == 0) {
+        if ((kflags & 8) && blockIdx.x == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             g_vqb_trace_vq[32 + i] = t;
         }
     };
     if (tid == 128) kmark(0);
-    if (tid == 128 && (p.flags & 8) && blockIdx.x < 256) {
+    if (tid == 128 && (kflags & 8) && blockIdx.x < 256) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_vqb_cta_t[2 * blockIdx.x] = t;
@@ -193,10 +197,10 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             auto drain = [&](int jt, long long jtile) {
                 const int zs = jt & 1;
                 ptx::mbar_wait(bar(Q_FULL + zs), (jt >> 1) & 1);
-                if (!(p.flags & 4)) {
+                if (!(kflags & 4)) {
                     const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
                     tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
-                    tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
+                    if (!p.zq_bf16) tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));     // (bf16: 64 channels = one atom)
                     bulk_commit();
                     bulk_wait_read0();
                 }
@@ -333,7 +337,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
             unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
-            const bool tr = kDebug == false && (p.flags & 8) && blockIdx.x == 0 && tid == 128;
+            const bool tr = kDebug == false && (kflags & 8) && blockIdx.x == 0 && tid == 128;
             vq_mark(tr, it, 0);
             ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
             vq_mark(tr, it, 1);
@@ -412,7 +416,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                         }
                     }
                 };
-                if (!(p.flags & 2)) {
+                if (!(kflags & 2)) {
                     ptx::tmem_ld32(tcol, va);
                     ptx::tmem_ld_wait32(va);
                     ptx::tmem_ld32(tcol + 32, vb);
@@ -527,7 +531,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
                 }
                 consider(M0, kg + j0); consider(M1, kg + j1); consider(M2, kg + j2); consider(M3, kg + j3);
             };
-            if (p.flags & 1) {
+            if (kflags & 1) {
                 bk = 0;                                         // timing experiment only
             } else if (!slow_row) {
                 // Both threads of the row walk BOTH compacted lists (their own, then the partner's, straight from
@@ -557,7 +561,37 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
             // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram ----
             const long long grow = tile * TM + row;
             {
+                auto emit_bf16 = [&](const float *zh) {
+                    // bf16 rows (128 B) written over the first atom of the z tile: this thread's 32 channels are the
+                    // four 16-byte pieces 4h .. 4h+3 (both threads of the row hold z in registers by now)
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float o[8];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int c16 = 2 * c8 + u;
+                            float4 e4;
+                            if (resident)
+                                e4 = *reinterpret_cast<const float4 *>(code_ptr_smem(bk) + h * EATOM + ((c16 ^ (bk & 7)) << 4));
+                            else
+                                e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)bk * DD + h * 32) + c16);
+                            float4 df;
+                            df.x = __fsub_rn(e4.x, zh[c16 * 4 + 0]); df.y = __fsub_rn(e4.y, zh[c16 * 4 + 1]);
+                            df.z = __fsub_rn(e4.z, zh[c16 * 4 + 2]); df.w = __fsub_rn(e4.w, zh[c16 * 4 + 3]);
+                            o[4 * u + 0] = __fadd_rn(zh[c16 * 4 + 0], df.x); o[4 * u + 1] = __fadd_rn(zh[c16 * 4 + 1], df.y);   // quantizer.py:67
+                            o[4 * u + 2] = __fadd_rn(zh[c16 * 4 + 2], df.z); o[4 * u + 3] = __fadd_rn(zh[c16 * 4 + 3], df.w);
+                            if (grow < p.N)
+                                sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
+                        }
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+                        *reinterpret_cast<uint4 *>(zrow + (((4 * h + c8) ^ rsw) << 4)) =
+                            make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                                       *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+                    }
+                };
                 auto emit = [&](const float *zh) {
+                    if (p.zq_bf16) { emit_bf16(zh); return; }
 #pragma unroll
                     for (int c16 = 0; c16 < 8; ++c16) {
                         float4 e4;
@@ -616,7 +650,7 @@ vq_tc_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CU
     ptx::tc_fence_before();
     __syncthreads();
     if (tid == 128) kmark(4);              // every warp done (producer drained its TMA stores)
-    if (tid == 128 && (p.flags & 8) && blockIdx.x < 256) {
+    if (tid == 128 && (kflags & 8) && blockIdx.x < 256) {
         unsigned long long t;
         unsigned sm_id;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -670,8 +704,8 @@ int launch_vq_reduce_sse(const void *ws, int K, double *sse, cudaStream_t s) {
 }
 
 // defer != 0: the SSE partials stay in the workspace (vqb_vq_reduce_sse_f32 sums them later, e.g. on a side stream)
-int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, float *zq, double *sse,
-                 int *hist, void *ws, float *dbg, int defer, cudaStream_t s) {
+int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long long *idx, void *zq, double *sse,
+                 int *hist, void *ws, float *dbg, int defer, int zq_bf16, cudaStream_t s) {
     if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
     const int nchunks = (K + CN - 1) / CN;
     const int Kpad = nchunks * CN;
@@ -687,8 +721,10 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     rc = vqb_encode_tmap_2d(&tme, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, E, DD, (uint64_t)K, DD * 4, 32, CN,
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, zq, DD, (uint64_t)N, DD * 4, 32, TM,
-                            CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = zq_bf16 ? vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq, DD, (uint64_t)N, DD * 2, 64, TM,
+                                      CU_TENSOR_MAP_SWIZZLE_128B)
+                 : vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, zq, DD, (uint64_t)N, DD * 4, 32, TM,
+                                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)K, s);
@@ -715,17 +751,17 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
     const long long ntiles = (N + TM - 1) / TM;
     int grid = (int)(ntiles < sms ? ntiles : sms);
     if (grid > 256) grid = 256;
-    if (const char *ge = getenv("VQB_TC_GRID")) { const int g = atoi(ge); if (g > 0 && g < grid) grid = g; }   // experiments
+    if (const char *ge = vqb_getenv("VQB_TC_GRID")) { const int g = atoi(ge); if (g > 0 && g < grid) grid = g; }   // experiments
     VqTcParams p;
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
-    p.idx = idx; p.partials = partials; p.hist = hist; p.dbg = dbg;
+    p.idx = idx; p.partials = partials; p.hist = hist; p.dbg = dbg; p.zq_bf16 = zq_bf16;
     p.pending = reinterpret_cast<unsigned *>(w + vq_ws_marker_offset(K));
     {
-        const char *fl = getenv("VQB_TC_FLAGS");
+        const char *fl = vqb_getenv("VQB_TC_FLAGS");
         p.flags = fl ? atoi(fl) : 0;
-        const char *tt = getenv("VQB_TC_TRACE_TILE");
-        if (tt && (p.flags & 8)) {
+        const char *tt = vqb_getenv("VQB_TC_TRACE_TILE");
+        if (tt && (kflags & 8)) {
             const int v = atoi(tt);
             cudaMemcpyToSymbolAsync(g_vqb_trace_tile, &v, sizeof(int), 0, cudaMemcpyHostToDevice, s);
         }

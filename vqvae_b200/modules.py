@@ -24,7 +24,8 @@ import torch.nn as nn
 
 from . import ops
 from .dist import reduce_vq_stats
-from ._lib import NCHW, NHWC, PRECISIONS
+from ._lib import (CONV_K1, CONV_K3, CONV_K4S2, CONVT_K3, CONVT_K4S2, CONVT_K4S2_OUT, NCHW, NHWC, PRECISIONS,
+                   RES_W2)
 
 _PRECISION = {"value": "fp32"}
 
@@ -51,22 +52,72 @@ def precision(name: str):
         set_precision(old)
 
 
-class _PackedWeights:
-    """Tap-major packed conv weights, cached ON the parameter object (so the cache dies with it:
-    a dict keyed by id(param) can hand a new model the stale packing of a freed one) and refreshed
-    when the parameter changes (load_state_dict / .to() / in-place edits bump ``_version`` or move
-    the storage)."""
+def _param_tag(param):
+    """Identity of a parameter's current value as far as torch tracks it.  ``.data`` edits (``w.data.mul_()``) do
+    not bump ``_version`` and inference-mode tensors have no version counter at all: call
+    ``vqvae_b200.invalidate_packed(model)`` after such edits (documented in INTEGRATION.md)."""
+    try:
+        ver = param._version
+    except RuntimeError:            # "Inference tensors do not track version counter"
+        ver = None
+    return (ver, param.data_ptr(), str(param.device))
 
-    def get(self, param, transposed):
-        tag = (param._version, param.data_ptr(), str(param.device), bool(transposed))
-        hit = getattr(param, "_vqb_packed", None)
-        if hit is None or hit[0] != tag:
-            hit = (tag, ops.pack_conv_weight(param, transposed))
-            param._vqb_packed = hit
-        return hit[1]
+
+class _PackedWeights:
+    """Packed conv weights cached ON the parameter object (so the cache dies with it) per packing kind:
+    ("f32", transposed) = the tap-major fp32 layouts of vqb_pack_conv_weight_f32, ("bf16", kind) = the k-step-ordered
+    bf16 layout of vqb_pack_conv_weight_bf16.  When the parameter changes (load_state_dict, optimizer step, .to())
+    the SAME device buffer is repacked in place whenever its size still fits, so CUDA graphs captured around a
+    forward keep reading current weights after ``repack`` (HostPipeline checks the tags before every replay)."""
+
+    def get(self, param, key):
+        tag = _param_tag(param)
+        cache = getattr(param, "_vqb_packed", None)
+        if cache is None:
+            cache = {}
+            param._vqb_packed = cache
+        hit = cache.get(key)
+        if hit is not None and hit[0] == tag and tag[0] is not None:
+            return hit[1]
+        old = hit[1] if hit is not None and hit[1] is not None and hit[1].device == param.device else None
+        if key[0] == "f32":
+            buf = ops.pack_conv_weight(param, key[1], out=old)
+        else:
+            buf = ops.pack_conv_weight_bf16(param, key[1], out=old)
+        cache[key] = (tag, buf)
+        return buf
+
+    def f32(self, param, transposed):
+        return self.get(param, ("f32", bool(transposed)))
+
+    def bf16(self, param, kind):
+        return self.get(param, ("bf16", int(kind)))
 
 
 _PACKED = _PackedWeights()
+
+
+def invalidate_packed(model):
+    """Drop every cached weight packing of ``model`` (after ``param.data`` edits, which torch does not version).
+    Buffers are kept and refilled in place at the next forward / ``HostPipeline.push``."""
+    for p in model.parameters():
+        cache = getattr(p, "_vqb_packed", None)
+        if cache:
+            for k, (tag, buf) in list(cache.items()):
+                cache[k] = ((None, None, None), buf)
+
+
+def packed_state(model):
+    """Tuple of the parameters' tags: changes whenever a weight packing may be stale."""
+    return tuple(_param_tag(p) for p in model.parameters())
+
+
+def _conv_precision():
+    """Arithmetic of the fp32-activation entry points (vqb_conv2d_f32 & co): "bf16" has no meaning for them -- bf16
+    operands exist only inside the fused VQVAE.forward / encode / decode pipeline -- so piecewise sub-module calls
+    run the TF32 kernels in that mode (more accurate than asked, never less)."""
+    name = get_precision()
+    return PRECISIONS["tf32" if name == "bf16" else name]
 
 
 def _bias(conv):
@@ -81,11 +132,11 @@ def _run_conv(conv, x, B, H, W, *, in_layout=NHWC, out_layout=NHWC, relu=False, 
     transposed = isinstance(conv, nn.ConvTranspose2d)
     kh, kw = conv.kernel_size
     stride, pad = conv.stride[0], conv.padding[0]
-    w = _PACKED.get(conv.weight, transposed)
+    w = _PACKED.f32(conv.weight, transposed)
     return ops.conv2d(x, w, _bias(conv), B=B, Cin=conv.in_channels, H=H, W=W, Cout=conv.out_channels,
                       kh=kh, kw=kw, stride=stride, pad=pad, transposed=transposed, in_layout=in_layout,
                       out_layout=out_layout, relu=relu, skip=skip,
-                      precision=PRECISIONS[get_precision()])
+                      precision=_conv_precision())
 
 
 def _prep_input(x, channels, what):
@@ -116,9 +167,9 @@ class ResidualLayer(nn.Module):
         """r = relu(x) in NHWC.  Returns r + W2.relu(W1 (*) r), optionally ReLU'd
         (the next consumer always applies ReLU first, residual.py:19,50)."""
         c1, c2 = self.res_block[1], self.res_block[3]
-        return ops.residual_layer(r, _PACKED.get(c1.weight, False), _PACKED.get(c2.weight, False), B=B, H=H, W=W,
+        return ops.residual_layer(r, _PACKED.f32(c1.weight, False), _PACKED.f32(c2.weight, False), B=B, H=H, W=W,
                                   C=c1.in_channels, Cmid=c1.out_channels, relu_out=relu_out,
-                                  precision=PRECISIONS[get_precision()])
+                                  precision=_conv_precision())
 
     def forward(self, x):
         xin = x
@@ -152,9 +203,27 @@ class ResidualStack(nn.Module):
                 r = l._apply_nhwc(r, B, H, W, relu_out=True)
             return r
         c1, c2 = layer.res_block[1], layer.res_block[3]
-        return ops.residual_stack(r, _PACKED.get(c1.weight, False), _PACKED.get(c2.weight, False), B=B, H=H, W=W,
+        return ops.residual_stack(r, _PACKED.f32(c1.weight, False), _PACKED.f32(c2.weight, False), B=B, H=H, W=W,
                                   C=c1.in_channels, Cmid=c1.out_channels, n_layers=len(self.stack),
-                                  precision=PRECISIONS[get_precision()])
+                                  precision=_conv_precision())
+
+    def _bf16_ok(self):
+        if len(self.stack) == 0:
+            return True
+        layer = self.stack[0]
+        c1 = layer.res_block[1]
+        return all(l is layer for l in self.stack) and c1.in_channels in (64, 128) and \
+            c1.out_channels % 16 == 0 and c1.out_channels <= 64
+
+    def _apply_nhwc_bf16(self, r, B, H, W):
+        """bf16 NHWC twin of _apply_nhwc: one persistent tcgen05 kernel per application of the shared layer."""
+        if len(self.stack) == 0:
+            return r
+        c1, c2 = self.stack[0].res_block[1], self.stack[0].res_block[3]
+        w1, w2 = _PACKED.bf16(c1.weight, CONV_K3), _PACKED.bf16(c2.weight, RES_W2)
+        for _ in range(len(self.stack)):
+            r = ops.residual_layer_bf16(r, w1, w2, B=B, H=H, W=W, C=c1.in_channels, Cmid=c1.out_channels, relu_out=True)
+        return r
 
     def forward(self, x):
         ch = self.stack[0].res_block[1].in_channels if len(self.stack) else x.shape[1]
@@ -199,6 +268,26 @@ class Encoder(nn.Module):
         h = cs[5]._apply_nhwc(h, B, H, W)
         return h, B, H, W
 
+    def _bf16_ok(self):
+        cs = self.conv_stack
+        return (cs[0].in_channels == 3 and cs[0].out_channels == 64 and cs[2].out_channels % 16 == 0
+                and cs[2].out_channels <= 256 and cs[4].in_channels % 64 == 0 and cs[4].in_channels <= 512
+                and cs[5]._bf16_ok())
+
+    def _forward_nhwc_bf16(self, x):
+        """VQB_BF16 pipeline: fp32 NCHW image -> bf16 NHWC latent activation (ReLU of the stack applied)."""
+        B, _, H, W = x.shape
+        cs = self.conv_stack
+        h = ops.conv_in_bf16(x, _PACKED.f32(cs[0].weight, False), _bias(cs[0]), B=B, H=H, W=W, Cout=cs[0].out_channels, relu=True)
+        H, W = H // 2, W // 2
+        h = ops.conv2d_bf16(h, _PACKED.bf16(cs[2].weight, CONV_K4S2), _bias(cs[2]), B=B, Cin=cs[2].in_channels, H=H, W=W,
+                            Cout=cs[2].out_channels, kind=CONV_K4S2, relu=True)
+        H, W = H // 2, W // 2
+        h = ops.conv2d_bf16(h, _PACKED.bf16(cs[4].weight, CONV_K3), _bias(cs[4]), B=B, Cin=cs[4].in_channels, H=H, W=W,
+                            Cout=cs[4].out_channels, kind=CONV_K3, relu=True)      # the stack's first ReLU folded in (Q2/Q3)
+        h = cs[5]._apply_nhwc_bf16(h, B, H, W)
+        return h, B, H, W
+
     def forward(self, x):
         x = _prep_input(x, self.conv_stack[0].in_channels, "Encoder")
         h, _, _, _ = self._forward_nhwc(x)
@@ -228,6 +317,24 @@ class Decoder(nn.Module):
         h = _run_conv(ics[2], h, B, H, W, relu=True)
         H, W = h.shape[1], h.shape[2]
         return _run_conv(ics[4], h, B, H, W, out_layout=NCHW)
+
+    def _bf16_ok(self):
+        ics = self.inverse_conv_stack
+        return (ics[0].in_channels % 64 == 0 and ics[0].out_channels % 16 == 0 and ics[0].out_channels <= 256
+                and ics[1]._bf16_ok() and ics[2].in_channels % 64 == 0 and ics[2].out_channels % 32 == 0
+                and ics[2].out_channels <= 128 and ics[4].in_channels % 64 == 0 and ics[4].out_channels <= 4)
+
+    def _forward_from_nhwc_bf16(self, z, B, H, W):
+        """z: bf16 NHWC (B,H,W,in_dim) -> x_hat fp32 NCHW, every layer on the bf16 tcgen05 kernels."""
+        ics = self.inverse_conv_stack
+        h = ops.conv2d_bf16(z, _PACKED.bf16(ics[0].weight, CONVT_K3), _bias(ics[0]), B=B, Cin=ics[0].in_channels, H=H, W=W,
+                            Cout=ics[0].out_channels, kind=CONVT_K3, relu=True)
+        h = ics[1]._apply_nhwc_bf16(h, B, H, W)
+        h = ops.conv2d_bf16(h, _PACKED.bf16(ics[2].weight, CONVT_K4S2), _bias(ics[2]), B=B, Cin=ics[2].in_channels, H=H, W=W,
+                            Cout=ics[2].out_channels, kind=CONVT_K4S2, relu=True)
+        H, W = 2 * H, 2 * W
+        return ops.conv2d_bf16(h, _PACKED.bf16(ics[4].weight, CONVT_K4S2_OUT), _bias(ics[4]), B=B, Cin=ics[4].in_channels,
+                               H=H, W=W, Cout=ics[4].out_channels, kind=CONVT_K4S2_OUT, relu=False)
 
     def forward(self, x):
         x = _prep_input(x, self.inverse_conv_stack[0].in_channels, "Decoder")
@@ -310,16 +417,38 @@ class VQVAE(nn.Module):
         self._side_stream = None
         self.last_min_encoding_indices = None
 
-    def _encode_rows(self, x):
+    def _bf16_pipeline(self):
+        """True when set_precision("bf16") is active AND every layer of this model has a bf16 tcgen05 kernel
+        (h_dim = 128 family: 64-channel first layer, channel counts in multiples of 64, embedding_dim = 64).
+        Other shapes run the TF32 kernels on fp32 activations, with a one-time warning."""
+        if get_precision() != "bf16":
+            return False
+        pq = self.pre_quantization_conv
+        ok = (self.encoder._bf16_ok() and self.decoder._bf16_ok() and pq.in_channels % 64 == 0
+              and pq.out_channels == 64 and self.vector_quantization.e_dim == 64)
+        if not ok and not getattr(self, "_warned_bf16", False):
+            import warnings
+            warnings.warn("vqvae_b200: this model shape has no bf16 kernels; precision 'bf16' runs the TF32 kernels")
+            self._warned_bf16 = True
+        return ok
+
+    def _encode_rows(self, x, bf16=False):
         x = _prep_input(x, 3, "VQVAE")
         if x.shape[2] % 4 or x.shape[3] % 4:
             raise RuntimeError("VQVAE: image height and width must be divisible by 4 (Q11)")
+        if bf16:
+            h, B, H, W = self.encoder._forward_nhwc_bf16(x)
+            pq = self.pre_quantization_conv
+            z_e = ops.conv2d_bf16(h, _PACKED.bf16(pq.weight, CONV_K1), _bias(pq), B=B, Cin=pq.in_channels, H=H, W=W,
+                                  Cout=pq.out_channels, kind=CONV_K1, relu=False, out_f32=True)   # fp32: feeds the exact VQ
+            return z_e, B, H, W
         h, B, H, W = self.encoder._forward_nhwc(x)
         z_e = _run_conv(self.pre_quantization_conv, h, B, H, W)              # NHWC (B,H,W,D)
         return z_e, B, H, W
 
     def forward(self, x, verbose=False):
-        z_e, B, H, W = self._encode_rows(x)                                  # vqvae.py:31-33
+        bf16 = self._bf16_pipeline()
+        z_e, B, H, W = self._encode_rows(x, bf16)                            # vqvae.py:31-33
         vq = self.vector_quantization
         D = vq.e_dim
         group = self.process_group
@@ -328,7 +457,10 @@ class VQVAE(nn.Module):
         # stream and overlap the decoder; fork/join with events, so the whole forward stays capturable in one
         # CUDA graph.
         n_rows = z_e.shape[0] * H * W
-        idx, zq, sse, hist, ws = ops.vq_forward(z_e.view(-1, D), vq._codebook(), defer=True)
+        if bf16:
+            idx, zq, sse, hist, ws = ops.vq_forward_bf16zq(z_e.view(-1, D), vq._codebook())
+        else:
+            idx, zq, sse, hist, ws = ops.vq_forward(z_e.view(-1, D), vq._codebook(), defer=True)
         main = torch.cuda.current_stream()
         if self._side_stream is None or self._side_stream.device != z_e.device:
             self._side_stream = torch.cuda.Stream(device=z_e.device)
@@ -340,7 +472,10 @@ class VQVAE(nn.Module):
             if not torch.cuda.is_current_stream_capturing():
                 for t in (ws, sse, hist, embedding_loss, perplexity):
                     t.record_stream(side)
-        x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
+        if bf16:
+            x_hat = self.decoder._forward_from_nhwc_bf16(zq.view(B, H, W, D), B, H, W)
+        else:
+            x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
         main.wait_stream(side)
         self.last_min_encoding_indices = idx.view(-1, 1)
         if verbose:                                                          # :38-42 (Q8)
@@ -353,7 +488,7 @@ class VQVAE(nn.Module):
     # ---- the two halves callers use around the path ----------
     def encode(self, x):
         """images -> min_encoding_indices (N,1) int64 (README step 2 / notebook cell 1)."""
-        z_e, B, H, W = self._encode_rows(x)
+        z_e, B, H, W = self._encode_rows(x, self._bf16_pipeline())
         _, _, _, idx = self.vector_quantization._quantize_rows(z_e.view(-1, self.vector_quantization.e_dim))
         return idx.view(-1, 1)
 
@@ -364,4 +499,6 @@ class VQVAE(nn.Module):
         vq = self.vector_quantization
         rows = ops.gather_rows(indices, vq._codebook())
         B = rows.shape[0] // (H * W)
+        if self._bf16_pipeline():
+            return self.decoder._forward_from_nhwc_bf16(rows.to(torch.bfloat16).view(B, H, W, vq.e_dim), B, H, W)
         return self.decoder._forward_from_nhwc(rows.view(B, H, W, vq.e_dim), B, H, W)

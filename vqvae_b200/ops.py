@@ -53,7 +53,7 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def pack_conv_weight(w, transposed):
+def pack_conv_weight(w, transposed, out=None):
     """(Cout,Cin,kh,kw) conv / (Cin,Cout,kh,kw) conv-transpose weight -> the two tap-major
     fp32 GEMM operand layouts of vqb_pack_conv_weight_f32, back to back:
     [(r*kw+s)*Cin+ci][co] for the FFMA kernel and [(r*kw+s)][co][ci] for tcgen05."""
@@ -64,7 +64,9 @@ def pack_conv_weight(w, transposed):
     else:
         cout, cin, kh, kw = w.shape
     # 2 GEMM layouts + (for the k4s2 output layer) the 9x16xCin pixel-shuffle packing
-    out = torch.empty((2 * kh * kw * cin * cout + 9 * 16 * cin,), dtype=torch.float32, device=w.device)
+    n = 2 * kh * kw * cin * cout + 9 * 16 * cin
+    if out is None or out.numel() != n or out.dtype != torch.float32 or out.device != w.device:
+        out = torch.empty((n,), dtype=torch.float32, device=w.device)      # else: repacked in place
     check(lib().vqb_pack_conv_weight_f32(w.data_ptr(), out.data_ptr(), cout, cin, kh, kw,
                                          int(bool(transposed)), _stream()), "pack_conv_weight")
     return out
@@ -119,7 +121,7 @@ def pack_conv_weight_bf16(w, kind, out=None):
     nbytes = lib().vqb_conv_bf16_packed_bytes(kind, cout, cin)
     if nbytes == 0:
         return None
-    if out is None:
+    if out is None or out.numel() != nbytes or out.dtype != torch.uint8 or out.device != w.device:
         # (torch's caching allocator hands out 512-byte aligned blocks: the 128-byte alignment the TMA maps need)
         out = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
     check(lib().vqb_pack_conv_weight_bf16(w.data_ptr(), out.data_ptr(), kind, cout, cin, _stream()), "pack_conv_weight_bf16")
@@ -147,6 +149,37 @@ def conv2d_bf16(x, packed, bias, *, B, Cin, H, W, Cout, kind, relu=False, out_f3
                                 _stream()), "conv2d_bf16")
     span.done()
     return out
+
+
+def conv_in_bf16(x, w_packed_f32, bias, *, B, H, W, Cout, relu=True):
+    """encoder.py:29-31 for the bf16 pipeline: fp32 NCHW image -> bf16 NHWC (B, H/2, W/2, Cout) (vqb_conv_in_bf16)."""
+    _require_cuda(x, "input")
+    out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device)
+    span = _Span(f"bf16 conv_in 3->{Cout} {H}x{W}")
+    check(lib().vqb_conv_in_bf16(x.data_ptr(), w_packed_f32.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                 out.data_ptr(), B, H, W, Cout, int(bool(relu)), _stream()), "conv_in_bf16")
+    span.done()
+    return out
+
+
+def vq_forward_bf16zq(z_rows, codebook):
+    """Fused VectorQuantizer core, fp32 rows in, bit-exact int64 idx, z_q as bf16 rows (vqb_vq_forward_bf16zq_f32).
+    Deferred SSE: returns (idx, zq_bf16, sse, hist, ws); run vq_reduce_sse(ws, ...) before reading sse."""
+    _require_cuda(z_rows, "z")
+    N, D = z_rows.shape
+    K = codebook.shape[0]
+    dev = z_rows.device
+    idx = torch.empty((N,), dtype=torch.int64, device=dev)
+    zq = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+    sse = torch.empty((1,), dtype=torch.float64, device=dev)
+    hist = torch.empty((K,), dtype=torch.int32, device=dev)
+    ws_bytes = lib().vqb_vq_workspace_bytes(N, K, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    span = _Span(f"vq N={N} K={K} D={D} (bf16 zq)")
+    check(lib().vqb_vq_forward_bf16zq_f32(z_rows.data_ptr(), codebook.data_ptr(), N, K, D, idx.data_ptr(), zq.data_ptr(),
+                                          sse.data_ptr(), hist.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "vq_forward_bf16zq")
+    span.done()
+    return idx, zq, sse, hist, ws
 
 
 def residual_layer_bf16(r, w1_packed, w2_packed, *, B, H, W, C, Cmid, relu_out):
