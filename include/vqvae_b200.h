@@ -198,9 +198,10 @@ int vqb_vq_forward_deferred_f32(const float *z, const float *codebook, int64_t N
 int vqb_vq_reduce_sse_f32(const void *workspace, int64_t N, int K, int D, double *sse,
                           void *stream);
 
-/* Kernel choice of vqb_vq_forward_f32: 0 = auto (tcgen05 kernel when D == 64, else the
- * exact FFMA kernel), 1 = always the FFMA kernel, 2 = require the tcgen05 kernel.  Both
- * produce bit-identical idx / zq; the switch exists for tests and benchmarks.        */
+/* Kernel choice of vqb_vq_forward_f32: 0 = auto (tcgen05 kernel when D == 64 and K <= 8192,
+ * else the exact FFMA kernel), 1 = always the FFMA kernel, 2 = require the tcgen05 kernel
+ * (vq2.cu), 3 = the round-1 tcgen05 kernel (vq_tc.cu, kept for comparison).  All produce
+ * bit-identical idx / zq; the switch exists for tests and benchmarks.                 */
 int vqb_set_vq_kernel(int which);
 
 /* Diagnostic twin of vqb_vq_forward_f32 (tcgen05 kernel only): additionally dumps the

@@ -20,4 +20,4 @@ restatements are pinned against outputs of the UNMODIFIED reference imported fro
 /root/reference in the authoring container; ``oracle/make_golden.py`` is the
 generating script and ``tests/golden/*.npz`` the committed vectors.
 """
-from .build import build, lib_path  # noqa: F401
+from .build import build, build_ref, lib_path, ref_path  # noqa: F401

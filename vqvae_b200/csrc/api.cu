@@ -16,6 +16,9 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
 int launch_conv_in_tc_ex(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int Cout,
                          int relu, int out_bf16, cudaStream_t s);
 
+bool vq2_supported(long long N, int K, int D);
+int launch_vq2(const float *z, const float *E, long long N, int K, int D, long long *idx, void *zq, double *sse, int *hist,
+               void *ws, int defer, int zq_bf16, cudaStream_t s);
 int launch_conv_in_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
                         int Cout, int relu, cudaStream_t s);
 int launch_convt_out_k4s2(const float *x, const float *wp, const float *bias, float *y, int B, int Cin, int H, int W,
@@ -49,9 +52,9 @@ int vqb_pdl_enabled() {
 }
 
 unsigned long long g_vqb_launches = 0;
-static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel
+static int g_vq_kernel = 0;   // 0 auto, 1 exact FFMA kernel, 2 tcgen05 kernel (vq2.cu), 3 round-1 tcgen05 kernel (vq_tc.cu)
 extern "C" int vqb_set_vq_kernel(int which) {
-    if (which < 0 || which > 2) return VQB_ERR_BAD_ARG;
+    if (which < 0 || which > 3) return VQB_ERR_BAD_ARG;
     g_vq_kernel = which;
     return 0;
 }
@@ -255,8 +258,12 @@ static int vq_forward_impl(const float *z, const float *codebook, int64_t N, int
     const uintptr_t al = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(codebook) |
                          reinterpret_cast<uintptr_t>(zq) | reinterpret_cast<uintptr_t>(workspace);
     if (al & 15) return VQB_ERR_ALIGNMENT;
-    const bool tc_ok = vq_tc_supported(N, K, D);
-    if (g_vq_kernel == 2 && !tc_ok) return VQB_ERR_UNSUPPORTED;
+    const bool tc_ok = vq_tc_supported(N, K, D), v2_ok = vq2_supported(N, K, D);
+    if (g_vq_kernel == 2 && !v2_ok) return VQB_ERR_UNSUPPORTED;
+    if (g_vq_kernel == 3 && !tc_ok) return VQB_ERR_UNSUPPORTED;
+    if (v2_ok && (g_vq_kernel == 0 || g_vq_kernel == 2))
+        return launch_vq2(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace, defer, 0,
+                          (cudaStream_t)stream);
     if (tc_ok && g_vq_kernel != 1)
         return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq, sse, hist, workspace,
                             nullptr, defer, 0, (cudaStream_t)stream);
@@ -279,6 +286,9 @@ extern "C" int vqb_vq_forward_bf16zq_f32(const float *z, const float *codebook, 
     const uintptr_t al = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(codebook) |
                          reinterpret_cast<uintptr_t>(zq_bf16) | reinterpret_cast<uintptr_t>(workspace);
     if (al & 15) return VQB_ERR_ALIGNMENT;
+    if (vq2_supported(N, K, D) && g_vq_kernel != 3)
+        return launch_vq2(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq_bf16, sse, hist, workspace, 1, 1,
+                          (cudaStream_t)stream);
     if (!vq_tc_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
     return launch_vq_tc(z, codebook, N, K, D, reinterpret_cast<long long *>(idx), zq_bf16, sse, hist, workspace, nullptr, 1, 1,
                         (cudaStream_t)stream);

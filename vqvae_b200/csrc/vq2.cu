@@ -1,0 +1,634 @@
+// vq2.cu -- fused VectorQuantizer.forward on tcgen05 (sm_100a), D = 64: second-generation epilogue.
+//
+// Replaces quantizer.py:45-71.  Same contract and the same arithmetic argument as vq_tc.cu (round 1): the TF32
+// scores s_k = ||e_k||^2 - 2 z.e_k only SELECT; tau bounds twice the worst-case error of a score, so every code whose
+// canonical fp32 distance could be the minimum -- the winner and all its ties -- has s_k <= min_k s_k + tau; codes
+// inside that window are re-scored with the canonical chain of oracle/csrc/oracle.c (sequential fmaf over d,
+// fl(fl(A+B) - fl(2M)), first minimum wins, NaN wins), so idx / z_q are bit-identical to vq_exact.cu and the oracle.
+//
+// What changed (profiles/r01_vq_tc_epilogue_timeline.txt: 8.7 us per 128-row tile against a 1.5 us HBM budget, all
+// phases serial, every row re-scoring 8-16 codes although 82-86 % of the rows have ONE code inside the window):
+//   * the sweep over the scores works at ELEMENT level: the code's position is packed into the low mantissa bits of
+//     its score (one LOP3; the perturbation, 2^-(23-nbits) relative, is added to tau) and every thread keeps 16
+//     (min, second-min) trackers, one per column residue mod 16 -- 4.75 instructions per score, no lists, no branches;
+//   * after the sweep a row's window is known exactly whenever no tracker holds TWO codes inside it (then a third
+//     might hide behind them): candidates = {tracker minima <= min + tau}.  One candidate -> it is the canonical
+//     argmin, NO exact arithmetic at all (the common case); 2..10 candidates -> those codes only are re-scored;
+//     two in one tracker (1/32 of the multi-candidate rows), non-finite data or overflow -> the row is queued and all
+//     finish threads scan the whole codebook for it together;
+//   * sweep (8 warps, TMEM readers) and finish (4 warps: decision, exact chains, gather, z_q = z + (e - z), SSE,
+//     histogram, idx) are different warps and work on different tiles at the same time; the TMA producer / MMA issuer
+//     run ahead of both.  16 warps per CTA, one CTA per SM, persistent.
+//   * z_q can leave as fp32 rows (module contract) or as bf16 rows (the bf16 decoder reads them; VQVAE.forward never
+//     returns z_q).
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int TM = 128;          // latent rows per tile (UMMA M)
+constexpr int CN = 256;          // codes per chunk (UMMA N)
+constexpr int DD = 64;
+constexpr int NT2 = 512;         // 16 warps
+constexpr int NTRK = 16;         // trackers per thread
+constexpr int MAXC = 5;          // candidates a half row can hand over
+constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
+constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
+constexpr int HIST_MAX = 1024;
+
+constexpr int OFF_Z = 0;
+constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
+constexpr int OFF_B = OFF_E + 2 * ESTAGE;                    // float[2 * CN]
+constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x 8 ints
+constexpr int OFF_XCH = OFF_CAND + 2 * 256 * 32;             // float2[256]: (half-row min, partial ||z||^2)
+constexpr int OFF_Q = OFF_XCH + 256 * 8;                     // full-scan queue: int[132] (count + rows)
+constexpr int OFF_QR = OFF_Q + 132 * 4;                      // per finish warp (d, k) partials: 4 x (float,int) x 8 slots
+constexpr int OFF_HIST = OFF_QR + 4 * 8 * 8;
+constexpr int OFF_BAR = OFF_HIST + HIST_MAX * 4;
+constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
+constexpr int OFF_RED = OFF_TMEM + 64;
+constexpr int SMEM_TOTAL = OFF_RED + 64;
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
+
+enum { Z_FULL = 0, Q_DONE = 2, E_FULL = 4, E_EMPTY = 6, T_FULL = 8, T_EMPTY = 10, C_FULL = 12, C_EMPTY = 14 };
+
+struct Vq2Params {
+    const float *E;        // (K, 64) codebook
+    const float *bn;       // (nchunks*256) canonical ||e_k||^2, +inf past K (streamed codebooks)
+    const float *scal;     // [0] = upper bound of max ||e_k||, [1] = non-finite flag (streamed codebooks)
+    long long N;
+    int K, nchunks, nbits;
+    long long *idx;
+    double *partials;
+    unsigned *pending;
+    int *hist;
+    int zq_bf16;
+};
+
+__device__ __forceinline__ bool vq2_better(float dn, int kn, float db, int kb) {
+    const bool nn = dn != dn, nb = db != db;            // torch.argmin: NaN is the minimum
+    if (nn || nb) return nn && (!nb || kn < kb);
+    return dn < db || (dn == db && kn < kb);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                     "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NT2, 1)
+vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme,
+           const __grid_constant__ CUtensorMap tmq, const Vq2Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (sbase - raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = sbase + OFF_BAR;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    float *bsm = reinterpret_cast<float *>(sm + OFF_B);
+    int *hist_s = reinterpret_cast<int *>(sm + OFF_HIST);
+    int *cand = reinterpret_cast<int *>(sm + OFF_CAND);
+    float2 *xch = reinterpret_cast<float2 *>(sm + OFF_XCH);
+    volatile int *fq = reinterpret_cast<volatile int *>(sm + OFF_Q);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
+
+    const long long ntiles = (p.N + TM - 1) / TM;
+    const int nchunks = p.nchunks;
+    const bool resident = nchunks <= 2;
+    const bool smem_hist = p.K <= HIST_MAX;
+    const float INF = __int_as_float(0x7f800000);
+
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tmz); ptx::prefetch_tmap(&tme); ptx::prefetch_tmap(&tmq);
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(bar(Z_FULL + s), 1);
+            ptx::mbar_init(bar(Q_DONE + s), 4);       // 4 finish warps
+            ptx::mbar_init(bar(E_FULL + s), 1);
+            ptx::mbar_init(bar(E_EMPTY + s), 9);      // MMA commit + 8 sweep warps
+            ptx::mbar_init(bar(T_FULL + s), 1);
+            ptx::mbar_init(bar(T_EMPTY + s), 8);
+            ptx::mbar_init(bar(C_FULL + s), 8);
+            ptx::mbar_init(bar(C_EMPTY + s), 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (smem_hist)
+        for (int k = tid; k < p.K; k += NT2) hist_s[k] = 0;
+    if (tid == 0) fq[0] = 0;
+    if (warp == 2) ptx::tmem_alloc(sbase + OFF_TMEM, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    pdl_launch_dependents();
+    pdl_wait();                    // z_e is written by the previous layer
+
+    auto code_ptr_smem = [&](int k) -> const unsigned char * { return sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128; };
+
+    if (warp == 0) {
+        // ===================== TMA producer (+ z_q tile stores) =====================
+        if (lane == 0) {
+            long long gc = 0;
+            int it = 0;
+            long long tile = blockIdx.x;
+            auto drain = [&](int jt, long long jtile) {      // z_q of tile jt is complete in its z stage: store it
+                const int zs = jt & 1;
+                ptx::mbar_wait(bar(Q_DONE + zs), (jt >> 1) & 1);
+                const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
+                tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
+                if (!p.zq_bf16) tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
+                bulk_commit();
+                bulk_wait_read0();
+            };
+            for (; tile < ntiles; tile += gridDim.x, ++it) {
+                const int zs = it & 1;
+                if (it >= 2) drain(it - 2, tile - 2 * (long long)gridDim.x);
+                ptx::mbar_expect_tx(bar(Z_FULL + zs), ZSTAGE);
+                const uint32_t zdst = sbase + OFF_Z + zs * ZSTAGE;
+                ptx::tma_load_2d(zdst, &tmz, bar(Z_FULL + zs), 0, (int)(tile * TM));
+                ptx::tma_load_2d(zdst + ZATOM, &tmz, bar(Z_FULL + zs), 32, (int)(tile * TM));
+                if (resident && it > 0) continue;
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int es = resident ? c : (int)(gc & 1);
+                    const uint32_t par = resident ? 0u : (uint32_t)((gc >> 1) & 1);
+                    ptx::mbar_wait(bar(E_EMPTY + es), par ^ 1);
+                    ptx::mbar_expect_tx(bar(E_FULL + es), resident ? ESTAGE : ESTAGE + CN * 4);
+                    const uint32_t edst = sbase + OFF_E + es * ESTAGE;
+                    ptx::tma_load_2d(edst, &tme, bar(E_FULL + es), 0, c * CN);
+                    ptx::tma_load_2d(edst + EATOM, &tme, bar(E_FULL + es), 32, c * CN);
+                    if (!resident)
+                        ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
+                }
+            }
+            for (int jt = (it >= 2 ? it - 2 : 0); jt < it; ++jt)
+                drain(jt, (long long)blockIdx.x + (long long)jt * gridDim.x);
+            bulk_wait_all0();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (converged warp, elected leader lane issues) =====================
+        const bool leader = ptx::elect_one();
+        constexpr uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, TM, CN);
+        const uint32_t d_hi = ptx::desc_hi_sw128(1024);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int zs = it & 1;
+            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            const uint32_t za_lo = (sbase + OFF_Z + zs * ZSTAGE) >> 4;
+            for (int c = 0; c < nchunks; ++c) {
+                const long long gc = (long long)it * nchunks + c;
+                int es;
+                if (resident) {
+                    es = c;
+                    if (it == 0) ptx::mbar_wait(bar(E_FULL + es), 0);
+                } else {
+                    es = (int)(gc & 1);
+                    ptx::mbar_wait(bar(E_FULL + es), (uint32_t)((gc >> 1) & 1));
+                }
+                const int ab = (int)(gc & 1);
+                ptx::mbar_wait(bar(T_EMPTY + ab), (uint32_t)(((gc >> 1) & 1) ^ 1));
+                ptx::tc_fence_after();
+                const uint32_t ea_lo = (sbase + OFF_E + es * ESTAGE) >> 4;
+#pragma unroll
+                for (int ks = 0; ks < DD / 8; ++ks)
+                    if (leader)
+                        ptx::mma_tf32_w(tmem_base + ab * CN, za_lo + (ks >> 2) * (ZATOM >> 4) + (ks & 3) * 2, d_hi,
+                                        ea_lo + (ks >> 2) * (EATOM >> 4) + (ks & 3) * 2, d_hi, idesc, ks > 0 ? 1u : 0u);
+                if (leader) {
+                    ptx::tc_commit(bar(T_FULL + ab));
+                    if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== sweep warps: thread = (row, column half) =====================
+        const int et = tid - 128;               // 0..255
+        const int q = warp & 3;                 // TMEM lane quadrant
+        const int h = (warp - 4) >> 2;          // column half of every chunk
+        const int row = q * 32 + lane;
+        const int rsw = row & 7;
+        float Emax;
+        bool bad_codebook;
+        if (resident) {
+            // canonical ||e_k||^2 (quantizer.py:50), their maximum and a non-finite flag from the resident copy
+            float mymax = 0.f;
+            unsigned mybad = 0u;
+            for (int c = 0; c < nchunks; ++c) ptx::mbar_wait(bar(E_FULL + c), 0);
+            for (int k = et; k < nchunks * CN; k += 256) {
+                float sn = INF;
+                if (k < p.K) {
+                    const unsigned char *er = sm + OFF_E + (k >> 8) * ESTAGE + (k & 255) * 128;
+                    sn = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 v = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ (k & 7)) << 4));
+                            sn = __fadd_rn(sn, __fmul_rn(v.x, v.x)); sn = __fadd_rn(sn, __fmul_rn(v.y, v.y));
+                            sn = __fadd_rn(sn, __fmul_rn(v.z, v.z)); sn = __fadd_rn(sn, __fmul_rn(v.w, v.w));
+                        }
+                    if (!(sn < INF)) mybad = 1u;
+                    else mymax = fmaxf(mymax, sqrtf(sn) * 1.00001f);
+                }
+                bsm[k] = sn;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, off));
+                mybad |= __shfl_xor_sync(0xffffffffu, mybad, off);
+            }
+            if (lane == 0) xch[warp - 4] = make_float2(mymax, __uint_as_float(mybad));
+            ptx::named_bar_sync(5, 256);
+            float mx = 0.f;
+            unsigned bad = 0u;
+            for (int w = 0; w < 8; ++w) { mx = fmaxf(mx, xch[w].x); bad |= __float_as_uint(xch[w].y); }
+            ptx::named_bar_sync(5, 256);
+            Emax = mx;
+            bad_codebook = bad != 0u;
+            if (et == 0) { fq[130] = __float_as_int(Emax); fq[131] = bad_codebook ? 1 : 0; }     // for the finish warps
+        } else {
+            Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
+            bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
+        }
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t keep = ~((1u << p.nbits) - 1u);
+
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int zs = it & 1;
+            const unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
+            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            // this thread's half of ||z||^2 (any order: it only feeds the error bound tau)
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+                const float4 v = *reinterpret_cast<const float4 *>(zrow + h * ZATOM + ((c16 ^ rsw) << 4));
+                a0 = fmaf(v.x, v.x, a0); a1 = fmaf(v.y, v.y, a1); a2 = fmaf(v.z, v.z, a2); a3 = fmaf(v.w, v.w, a3);
+            }
+            const float Apart = (a0 + a1) + (a2 + a3);
+
+            float m1[NTRK], m2[NTRK];
+#pragma unroll
+            for (int i = 0; i < NTRK; ++i) { m1[i] = INF; m2[i] = INF; }
+
+            for (int c = 0; c < nchunks; ++c) {
+                const long long gc = (long long)it * nchunks + c;
+                const int ab = (int)(gc & 1);
+                const int es = resident ? c : (int)(gc & 1);
+                ptx::mbar_wait(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1));
+                ptx::tc_fence_after();
+                const float *bch = bsm + es * CN + h * 128;
+                const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
+                const uint32_t cbase = (uint32_t)(c * 128);
+                float va[32], vb[32];
+                auto process = [&](const float (&v)[32], int j) {
+                    const uint32_t jb = cbase + (uint32_t)(j * 32);
+                    float bq[32];                                     // ||e_k||^2 of the 32 columns (broadcast 16-byte loads)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bch + j * 32 + 4 * i);
+                        bq[4 * i] = b4.x; bq[4 * i + 1] = b4.y; bq[4 * i + 2] = b4.z; bq[4 * i + 3] = b4.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NTRK; ++i) {
+                        // scores of columns i and i+16 of this load, position packed into the low mantissa bits
+                        const float sa = fmaf(v[i], -2.f, bq[i]);
+                        const float sb = fmaf(v[i + 16], -2.f, bq[i + 16]);
+                        const float pa = __uint_as_float((__float_as_uint(sa) & keep) | (jb + (uint32_t)i));
+                        const float pb = __uint_as_float((__float_as_uint(sb) & keep) | (jb + (uint32_t)(i + 16)));
+                        const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+                        const float t = fmaxf(m1[i], lo);
+                        m1[i] = fminf(m1[i], lo);
+                        m2[i] = ptx::fmin3(t, m2[i], hi);
+                    }
+                };
+                ptx::tmem_ld32(tcol, va);
+                ptx::tmem_ld_wait32(va);
+                ptx::tmem_ld32(tcol + 32, vb);
+                process(va, 0);
+                ptx::tmem_ld_wait32(vb);
+                ptx::tmem_ld32(tcol + 64, va);
+                process(vb, 1);
+                ptx::tmem_ld_wait32(va);
+                ptx::tmem_ld32(tcol + 96, vb);
+                process(va, 2);
+                ptx::tmem_ld_wait32(vb);
+                process(vb, 3);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(bar(T_EMPTY + ab));
+                    if (!resident) ptx::mbar_arrive(bar(E_EMPTY + es));
+                }
+            }
+
+            // ---- half-row minimum, exchange with the partner thread (same row, other column half) ----
+            float hmin = m1[0];
+#pragma unroll
+            for (int i = 1; i < NTRK; ++i) hmin = fminf(hmin, m1[i]);
+            xch[et] = make_float2(hmin, Apart);
+            ptx::named_bar_sync(1 + q, 64);
+            const float2 px = xch[et ^ 128];
+            const float rowmin = fminf(hmin, px.x);
+            const float A = Apart + px.y;
+            // S >= sum_d |z_d e_kd| for every k (Cauchy-Schwarz, rounded up); tau = 2 x (tf32 truncation of both
+            // operands on 2M: 2*2^-9*S, fp32 accumulation + the canonical formula's own rounding, the index packing:
+            // 2^-(23-nbits) of |s| <= Emax^2 + 2S), with margin.
+            const float S = sqrtf(A) * 1.00002f * Emax;
+            const float pack_eps = __int_as_float((127 - (23 - p.nbits)) << 23);       // 2^-(23-nbits)
+            const float tau = S * (0.0078125f + 0.0009765625f) + (A + Emax * Emax + S) * 1.9073486e-6f +
+                              2.f * pack_eps * (Emax * Emax + 2.f * S) * 1.01f + 1e-30f;
+            const bool slow_row = bad_codebook || !(A < INF) || !(tau < INF) || !(rowmin == rowmin);
+            const float thr = rowmin + tau;
+            ptx::named_bar_sync(1 + q, 64);               // xch is reused by the next tile
+
+            // ---- this half's candidates: tracker minima inside the window; a tracker with TWO codes inside it may
+            // hide a third -> the row needs the whole-codebook scan ----
+            int n = 0;
+            bool needfull = slow_row;
+            int ids[MAXC];
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) ids[i] = 0;
+#pragma unroll
+            for (int i = 0; i < NTRK; ++i) {
+                if (m1[i] <= thr) {
+                    const uint32_t pos = __float_as_uint(m1[i]) & ~keep;          // chunk * 128 + position in the half
+                    const int k = (int)((pos >> 7) * CN + (uint32_t)(h * 128) + (pos & 127u));
+                    if (k >= p.K) needfull = true;                                 // (a padding column: only when every score is +inf)
+                    if (n < MAXC) {
+#pragma unroll
+                        for (int s = 0; s < MAXC; ++s) if (s == n) ids[s] = k;
+                    } else needfull = true;
+                    ++n;
+                }
+                if (m2[i] <= thr) needfull = true;
+            }
+            const int par = it & 1;
+            ptx::mbar_wait(bar(C_EMPTY + par), (uint32_t)(((it >> 1) & 1) ^ 1));       // finish warps are done with tile it-2's records
+            int *rec = cand + (par * 256 + et) * 8;
+            rec[0] = needfull ? -1 : n;
+#pragma unroll
+            for (int s = 0; s < MAXC; ++s) rec[1 + s] = ids[s];
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(C_FULL + par));
+        }
+    } else if (warp >= 12) {
+        // ===================== finish warps: thread = row =====================
+        const int ft = tid - 384;               // 0..127 = row of the tile
+        const int row = ft, rsw = row & 7;
+        double sse = 0.0;
+        float *qr = reinterpret_cast<float *>(sm + OFF_QR);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int zs = it & 1, par = it & 1;
+            unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
+            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            ptx::mbar_wait(bar(C_FULL + par), (uint32_t)((it >> 1) & 1));
+            float Emax = 0.f;
+            (void)Emax;
+            // z row -> registers
+            float zr[DD];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ rsw) << 4));
+                    zr[a * 32 + c16 * 4 + 0] = v.x; zr[a * 32 + c16 * 4 + 1] = v.y;
+                    zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
+                }
+            const int *r0 = cand + (par * 256 + row) * 8, *r1 = cand + (par * 256 + 128 + row) * 8;
+            const int n0 = r0[0], n1 = r1[0];
+            int bk = -1;
+            float bd = 0.f;
+            // canonical A_i = sum_d fl(z^2), left to right (quantizer.py:49) -- needed by every exact distance
+            float A = 0.f;
+#pragma unroll
+            for (int d = 0; d < DD; ++d) A = __fadd_rn(A, __fmul_rn(zr[d], zr[d]));
+            auto exact_code = [&](int k) {       // canonical distance of code k; keeps the better of (bd,bk) and it
+                float M = 0.f;
+                float bnk;
+                if (resident) {
+                    const unsigned char *er = code_ptr_smem(k);
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 e = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ (k & 7)) << 4));
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 0], e.x, M); M = __fmaf_rn(zr[a * 32 + c16 * 4 + 1], e.y, M);
+                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 2], e.z, M); M = __fmaf_rn(zr[a * 32 + c16 * 4 + 3], e.w, M);
+                        }
+                    bnk = bsm[k];
+                } else {
+                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);
+#pragma unroll
+                    for (int c16 = 0; c16 < 16; ++c16) {
+                        const float4 e = __ldg(er + c16);
+                        M = __fmaf_rn(zr[c16 * 4 + 0], e.x, M); M = __fmaf_rn(zr[c16 * 4 + 1], e.y, M);
+                        M = __fmaf_rn(zr[c16 * 4 + 2], e.z, M); M = __fmaf_rn(zr[c16 * 4 + 3], e.w, M);
+                    }
+                    bnk = __ldg(p.bn + k);
+                }
+                const float dist = __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));   // quantizer.py:49-51
+                if (bk < 0 || vq2_better(dist, k, bd, bk)) { bd = dist; bk = k; }
+            };
+            const bool queued = n0 < 0 || n1 < 0;
+            if (queued) {
+                const int slot = atomicAdd(const_cast<int *>(&fq[0]), 1);
+                fq[1 + slot] = row;
+            } else if (n0 + n1 == 1) {
+                bk = n0 == 1 ? r0[1] : r1[1];            // the only code inside the window: provably the canonical argmin
+            } else {
+                for (int s = 0; s < n0; ++s) { const int k = r0[1 + s]; if (k < p.K) exact_code(k); }
+                for (int s = 0; s < n1; ++s) { const int k = r1[1 + s]; if (k < p.K) exact_code(k); }
+            }
+            ptx::named_bar_sync(6, 128);                   // the queue is complete
+            const int nq = fq[0];
+            if (nq > 0) {
+                // whole-codebook exact scans, all 128 finish threads per queued row: thread t takes codes t, t+128, ...
+                for (int qi = 0; qi < nq; ++qi) {
+                    const int qrow = fq[1 + qi];
+                    const unsigned char *qz = sm + OFF_Z + zs * ZSTAGE + qrow * 128;
+                    float qA = 0.f;
+                    // canonical norm of the queued row (broadcast loads)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {
+                            const float4 v = *reinterpret_cast<const float4 *>(qz + a * ZATOM + ((c16 ^ (qrow & 7)) << 4));
+                            qA = __fadd_rn(qA, __fmul_rn(v.x, v.x)); qA = __fadd_rn(qA, __fmul_rn(v.y, v.y));
+                            qA = __fadd_rn(qA, __fmul_rn(v.z, v.z)); qA = __fadd_rn(qA, __fmul_rn(v.w, v.w));
+                        }
+                    float sd = 0.f;
+                    int sk = -1;
+                    for (int k = ft; k < p.K; k += 128) {
+                        float M = 0.f;
+                        const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);     // (L2; rare path)
+#pragma unroll
+                        for (int c16 = 0; c16 < 16; ++c16) {
+                            const float4 e = __ldg(er + c16);
+                            const float4 v = *reinterpret_cast<const float4 *>(qz + (c16 >> 3) * ZATOM + (((c16 & 7) ^ (qrow & 7)) << 4));
+                            M = __fmaf_rn(v.x, e.x, M); M = __fmaf_rn(v.y, e.y, M); M = __fmaf_rn(v.z, e.z, M); M = __fmaf_rn(v.w, e.w, M);
+                        }
+                        const float bnk = resident ? bsm[k] : __ldg(p.bn + k);
+                        const float dist = __fsub_rn(__fadd_rn(qA, bnk), __fmul_rn(2.0f, M));
+                        if (sk < 0 || vq2_better(dist, k, sd, sk)) { sd = dist; sk = k; }
+                    }
+                    // warp reduce, then 4 warp partials through shared memory
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const float od = __shfl_xor_sync(0xffffffffu, sd, off);
+                        const int ok = __shfl_xor_sync(0xffffffffu, sk, off);
+                        if (ok >= 0 && (sk < 0 || vq2_better(od, ok, sd, sk))) { sd = od; sk = ok; }
+                    }
+                    if (lane == 0) { qr[((warp - 12) * 8 + (qi & 7)) * 2] = sd; reinterpret_cast<int *>(qr)[((warp - 12) * 8 + (qi & 7)) * 2 + 1] = sk; }
+                    ptx::named_bar_sync(6, 128);
+                    if (row == qrow) {
+                        for (int w = 0; w < 4; ++w) {
+                            const float od = qr[(w * 8 + (qi & 7)) * 2];
+                            const int ok = reinterpret_cast<int *>(qr)[(w * 8 + (qi & 7)) * 2 + 1];
+                            if (ok >= 0 && (bk < 0 || vq2_better(od, ok, bd, bk))) { bd = od; bk = ok; }
+                        }
+                    }
+                    if ((qi & 7) == 7) ptx::named_bar_sync(6, 128);      // the 8 partial slots are recycled
+                }
+                ptx::named_bar_sync(6, 128);
+                if (ft == 0) fq[0] = 0;
+                ptx::named_bar_sync(6, 128);               // (the reset is visible before any push of the next tile)
+            }
+            if (bk < 0) bk = 0;
+
+            // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram, idx ----
+            const long long grow = tile * TM + row;
+            const bool live = grow < p.N;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float o[8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c16 = 2 * c8 + u;                  // 16-byte piece of the 256-byte fp32 row
+                    float4 e4;
+                    if (resident) e4 = *reinterpret_cast<const float4 *>(code_ptr_smem(bk) + (c16 >> 3) * EATOM + (((c16 & 7) ^ (bk & 7)) << 4));
+                    else e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)bk * DD) + c16);
+                    float4 df;
+                    df.x = __fsub_rn(e4.x, zr[c16 * 4 + 0]); df.y = __fsub_rn(e4.y, zr[c16 * 4 + 1]);
+                    df.z = __fsub_rn(e4.z, zr[c16 * 4 + 2]); df.w = __fsub_rn(e4.w, zr[c16 * 4 + 3]);
+                    o[4 * u + 0] = __fadd_rn(zr[c16 * 4 + 0], df.x); o[4 * u + 1] = __fadd_rn(zr[c16 * 4 + 1], df.y);     // quantizer.py:67
+                    o[4 * u + 2] = __fadd_rn(zr[c16 * 4 + 2], df.z); o[4 * u + 3] = __fadd_rn(zr[c16 * 4 + 3], df.w);
+                    if (live) sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
+                    if (!p.zq_bf16)
+                        *reinterpret_cast<float4 *>(zrow + (c16 >> 3) * ZATOM + (((c16 & 7) ^ rsw) << 4)) =
+                            make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+                }
+                if (p.zq_bf16) {
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+                    *reinterpret_cast<uint4 *>(zrow + ((c8 ^ rsw) << 4)) =
+                        make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                                   *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+                }
+            }
+            if (live) {
+                p.idx[grow] = bk;
+                if (smem_hist) atomicAdd(&hist_s[bk], 1);
+                else atomicAdd(&p.hist[bk], 1);
+            }
+            ptx::fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) { ptx::mbar_arrive(bar(Q_DONE + zs)); ptx::mbar_arrive(bar(C_EMPTY + par)); }
+        }
+        // ---- CTA reduction of the SSE partial, histogram flush ----
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, off);
+        double *red = reinterpret_cast<double *>(sm + OFF_RED);
+        if (lane == 0) red[warp - 12] = sse;
+        ptx::named_bar_sync(6, 128);
+        if (ft == 0) {
+            p.partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+            if (blockIdx.x == 0) *p.pending = gridDim.x;
+        }
+        if (smem_hist)
+            for (int k = ft; k < p.K; k += 128) {
+                const int cval = hist_s[k];
+                if (cval) atomicAdd(&p.hist[k], cval);
+            }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool vq2_supported(long long N, int K, int D) {
+    return D == DD && N >= 1 && N < (1LL << 31) && K >= 1 && K <= 8192;
+}
+
+size_t vq_ws_marker_offset(int K);
+size_t vq_tc_workspace_bytes(int K);
+void vq_tc_prep(const float *E, int K, int Kpad, float *bn, unsigned *scal, cudaStream_t s);
+void vq_tc_sum(const double *partials, int n, double *out, cudaStream_t s);
+
+// workspace layout = vq_tc.cu's: [bn: Kpad floats][scal: 256 B][partials: 256 doubles]
+int launch_vq2(const float *z, const float *E, long long N, int K, int D, long long *idx, void *zq, double *sse, int *hist,
+               void *ws, int defer, int zq_bf16, cudaStream_t s) {
+    if (!vq2_supported(N, K, D)) return VQB_ERR_UNSUPPORTED;
+    const int nchunks = (K + CN - 1) / CN;
+    const int Kpad = nchunks * CN;
+    auto align256 = [](size_t x) { return (x + 255) / 256 * 256; };
+    unsigned char *w = reinterpret_cast<unsigned char *>(ws);
+    float *bn = reinterpret_cast<float *>(w);
+    unsigned *scal = reinterpret_cast<unsigned *>(w + align256((size_t)Kpad * 4));
+    double *partials = reinterpret_cast<double *>(w + align256((size_t)Kpad * 4) + 256);
+
+    CUtensorMap tmz, tme, tmq;
+    int rc = vqb_encode_tmap_2d(&tmz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, z, DD, (uint64_t)N, DD * 4, 32, TM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = vqb_encode_tmap_2d(&tme, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, E, DD, (uint64_t)K, DD * 4, 32, CN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = zq_bf16 ? vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq, DD, (uint64_t)N, DD * 2, 64, TM, CU_TENSOR_MAP_SWIZZLE_128B)
+                 : vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, zq, DD, (uint64_t)N, DD * 4, 32, TM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+
+    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)K, s);
+    if (e != cudaSuccess) return (int)e;
+    int nlaunch = 2;
+    if (nchunks > 2) {          // streamed codebook: norms / max / flag from a prep launch
+        e = cudaMemsetAsync(scal, 0, 256, s);
+        if (e != cudaSuccess) return (int)e;
+        vq_tc_prep(E, K, Kpad, bn, scal, s);
+        nlaunch = 3;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(vq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (N + TM - 1) / TM;
+    int grid = (int)(ntiles < sms ? ntiles : sms);
+    if (grid > 256) grid = 256;
+    Vq2Params p;
+    p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
+    p.N = N; p.K = K; p.nchunks = nchunks;
+    p.nbits = 7;
+    while ((1 << p.nbits) < nchunks * 128) ++p.nbits;       // position of a code inside one thread's half: chunk * 128 + column
+    p.idx = idx; p.partials = partials; p.hist = hist; p.zq_bf16 = zq_bf16;
+    p.pending = reinterpret_cast<unsigned *>(w + vq_ws_marker_offset(K));
+    if (cudaError_t le = vqb_launch(vq2_kernel, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)) return (int)le;
+    if (!defer) vq_tc_sum(partials, grid, sse, s);
+    VQB_COUNT_LAUNCH(defer ? nlaunch - 1 : nlaunch);
+    return vqb_cuda_status(cudaGetLastError());
+}

@@ -681,6 +681,14 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
 
+// shared with vq2.cu (same workspace layout)
+void vq_tc_prep(const float *E, int K, int Kpad, float *bn, unsigned *scal, cudaStream_t s) {
+    vq_tc_prep_kernel<<<(Kpad + 127) / 128, 128, 0, s>>>(E, K, Kpad, bn, scal);
+}
+void vq_tc_sum(const double *partials, int n, double *out, cudaStream_t s) {
+    vq_tc_sum_partials<<<1, 256, 0, s>>>(partials, n, nullptr, out);
+}
+
 // workspace: [bn: Kpad floats][scal: 256 B][partials: 256 doubles]
 size_t vq_tc_workspace_bytes(int K) {
     const size_t Kpad = (size_t)((K + CN - 1) / CN) * CN;
@@ -761,7 +769,7 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
         const char *fl = vqb_getenv("VQB_TC_FLAGS");
         p.flags = fl ? atoi(fl) : 0;
         const char *tt = vqb_getenv("VQB_TC_TRACE_TILE");
-        if (tt && (kflags & 8)) {
+        if (tt && (p.flags & 8)) {
             const int v = atoi(tt);
             cudaMemcpyToSymbolAsync(g_vqb_trace_tile, &v, sizeof(int), 0, cudaMemcpyHostToDevice, s);
         }

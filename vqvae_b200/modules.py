@@ -97,9 +97,13 @@ class _PackedWeights:
 _PACKED = _PackedWeights()
 
 
+_INVALIDATIONS = {"n": 0}
+
+
 def invalidate_packed(model):
     """Drop every cached weight packing of ``model`` (after ``param.data`` edits, which torch does not version).
     Buffers are kept and refilled in place at the next forward / ``HostPipeline.push``."""
+    _INVALIDATIONS["n"] += 1
     for p in model.parameters():
         cache = getattr(p, "_vqb_packed", None)
         if cache:
@@ -414,6 +418,11 @@ class VQVAE(nn.Module):
         # batch-sharded inference: set to a torch.distributed process group so that
         # embedding_loss / perplexity equal the single-process values
         self.process_group = None
+        # True: every sharded forward all-reduces the VQ statistics (one 4 KB collective per step: every step is a
+        # rank rendezvous).  False: forward returns THIS SHARD's loss / perplexity and keeps the statistics;
+        # reduce_scalars() all-reduces them on demand (e.g. every M steps, or when a caller reads the scalars).
+        self.sync_scalars = True
+        self.last_vq_stats = None            # (hist int32 (K,), sse f64 (1,), rows of this shard) of the last forward
         self._side_stream = None
         self.last_min_encoding_indices = None
 
@@ -468,7 +477,8 @@ class VQVAE(nn.Module):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             ops.vq_reduce_sse(ws, n_rows, vq.n_e, D, sse)
-            embedding_loss, perplexity = vq._scalars(sse, hist, n_rows, group)
+            embedding_loss, perplexity = vq._scalars(sse, hist, n_rows, group if self.sync_scalars else None)
+            self.last_vq_stats = (hist, sse, n_rows)
             if not torch.cuda.is_current_stream_capturing():
                 for t in (ws, sse, hist, embedding_loss, perplexity):
                     t.record_stream(side)
@@ -484,6 +494,38 @@ class VQVAE(nn.Module):
             print('recon data shape:', x_hat.shape)
             assert False
         return embedding_loss, x_hat, perplexity
+
+    def reduce_scalars(self):
+        """(embedding_loss, perplexity) over the WHOLE sharded batch from the statistics of the last forward: the one
+        collective of the path, issued on demand when ``sync_scalars`` is False.  Equals the
+        single-process values on the concatenated batch (tests/test_dist_cpu.py, tests/test_gpu_dist.py)."""
+        if self.last_vq_stats is None:
+            raise RuntimeError("reduce_scalars: no forward has run yet")
+        hist, sse, n_rows = self.last_vq_stats
+        return self.vector_quantization._scalars(sse, hist, n_rows, self.process_group)
+
+    def repack(self):
+        """Refresh every cached weight packing whose parameter changed (load_state_dict, optimizer step), IN PLACE
+        in the buffers earlier forwards -- and CUDA graphs captured around them -- already read.  A plain forward
+        does this by itself; HostPipeline calls it before replaying a captured graph."""
+        enc, dec, pq = self.encoder.conv_stack, self.decoder.inverse_conv_stack, self.pre_quantization_conv
+        bf16 = self._bf16_pipeline()
+        _PACKED.f32(enc[0].weight, False)
+        stacks = [s for s in (enc[5], dec[1]) if len(s.stack)]
+        if bf16:
+            _PACKED.bf16(enc[2].weight, CONV_K4S2); _PACKED.bf16(enc[4].weight, CONV_K3); _PACKED.bf16(pq.weight, CONV_K1)
+            _PACKED.bf16(dec[0].weight, CONVT_K3); _PACKED.bf16(dec[2].weight, CONVT_K4S2)
+            _PACKED.bf16(dec[4].weight, CONVT_K4S2_OUT)
+            for st in stacks:
+                _PACKED.bf16(st.stack[0].res_block[1].weight, CONV_K3); _PACKED.bf16(st.stack[0].res_block[3].weight, RES_W2)
+        else:
+            for conv in (enc[2], enc[4], pq):
+                _PACKED.f32(conv.weight, False)
+            for conv in (dec[0], dec[2], dec[4]):
+                _PACKED.f32(conv.weight, True)
+            for st in stacks:
+                for layer in set(st.stack):
+                    _PACKED.f32(layer.res_block[1].weight, False); _PACKED.f32(layer.res_block[3].weight, False)
 
     # ---- SURVEY 8(f) rank 1: the two halves callers use around the path ----------
     def encode(self, x):

@@ -143,7 +143,9 @@ def conv2d_bf16(x, packed, bias, *, B, Cin, H, W, Cout, kind, relu=False, out_f3
     else:
         shape, dt = (B, H, W, Cout), (torch.float32 if out_f32 else torch.bfloat16)
     out = torch.empty(shape, dtype=dt, device=x.device)
-    span = _Span(f"bf16 kind{kind} {Cin}->{Cout} {H}x{W}")
+    k, st, tr = {_lib.CONV_K1: (1, 1, ""), _lib.CONV_K3: (3, 1, ""), _lib.CONVT_K3: (3, 1, "T"), _lib.CONV_K4S2: (4, 2, ""),
+                 _lib.CONVT_K4S2: (4, 2, "T"), _lib.CONVT_K4S2_OUT: (4, 2, "T")}[kind]
+    span = _Span(f"bf16 conv{tr} {Cin}->{Cout} k{k}s{st} {H}x{W}")
     check(lib().vqb_conv2d_bf16(x.data_ptr(), packed.data_ptr(), bias.data_ptr() if bias is not None else None,
                                 out.data_ptr(), B, Cin, H, W, Cout, kind, int(bool(relu)), int(bool(out_f32)),
                                 _stream()), "conv2d_bf16")
@@ -155,7 +157,7 @@ def conv_in_bf16(x, w_packed_f32, bias, *, B, H, W, Cout, relu=True):
     """encoder.py:29-31 for the bf16 pipeline: fp32 NCHW image -> bf16 NHWC (B, H/2, W/2, Cout) (vqb_conv_in_bf16)."""
     _require_cuda(x, "input")
     out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device)
-    span = _Span(f"bf16 conv_in 3->{Cout} {H}x{W}")
+    span = _Span(f"bf16 conv 3->{Cout} k4s2 {H}x{W}")
     check(lib().vqb_conv_in_bf16(x.data_ptr(), w_packed_f32.data_ptr(), bias.data_ptr() if bias is not None else None,
                                  out.data_ptr(), B, H, W, Cout, int(bool(relu)), _stream()), "conv_in_bf16")
     span.done()
@@ -301,7 +303,7 @@ def relu_(x):
     return x
 
 
-VQ_KERNELS = {"auto": 0, "exact": 1, "tc": 2}
+VQ_KERNELS = {"auto": 0, "exact": 1, "tc": 2, "tc_r1": 3}
 
 
 def set_vq_kernel(name: str):

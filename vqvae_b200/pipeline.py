@@ -27,6 +27,7 @@ from typing import Deque, List, Optional
 import torch
 
 from ._lib import check, lib
+from .modules import _INVALIDATIONS
 
 
 @dataclass
@@ -106,12 +107,36 @@ class HostPipeline:
             # depth in flight + the one whose result the caller is still reading
             self._slots = [_Slot(model, self.shape, self.device, use_graph) for _ in range(depth + 1)]
         self.depth = depth
+        self.model = model
+        self._params = list(model.parameters())
+        self._pstate = self._param_versions()
         self._inflight: Deque[_Slot] = deque()
         self._count = 0
         self._lib = lib()
         self._raw = bool(raw_copies)
 
     # -- internals ---------------------------------------------------------------------------
+    def _param_versions(self):
+        try:
+            return (_INVALIDATIONS["n"],) + tuple((p._version, p.data_ptr()) for p in self._params)
+        except RuntimeError:                     # inference tensors carry no version counter: always refresh
+            return None
+
+    def _refresh_weights(self):
+        """The captured graphs read the packed-weight buffers, which only a Python-side forward refreshes: after a
+        load_state_dict / optimizer step, repack IN PLACE (same buffers) on the compute stream before the next replay
+        (``param.data`` edits are invisible to torch's version counters: call vqvae_b200.invalidate_packed first)."""
+        st = self._param_versions()
+        if st is not None and st == self._pstate:
+            return
+        prev = torch.cuda.current_stream(self.device)
+        torch.cuda.set_stream(self._compute)
+        try:
+            self.model.repack()
+        finally:
+            torch.cuda.set_stream(prev)
+        self._pstate = st
+
     def _finish(self, slot: _Slot) -> HostResult:
         slot.d2h_done.synchronize()
         slot.busy = False
@@ -126,6 +151,7 @@ class HostPipeline:
         done = None
         if len(self._inflight) == self.depth:
             done = self._finish(self._inflight.popleft())
+        self._refresh_weights()
         slot = self._slots[self._count % len(self._slots)]
         assert not slot.busy
         slot.busy, slot.index = True, self._count
