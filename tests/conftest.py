@@ -15,3 +15,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _fp32_unless_stated():
+    """The parity tests were written against the all-fp32 (FFMA) arithmetic and state any other mode explicitly
+    (``with vqvae_b200.precision("tf32")``); the package default is "tf32" (tests/test_abi_cpu.py checks that)."""
+    import vqvae_b200
+    vqvae_b200.set_precision("fp32")
+    yield
+    vqvae_b200.set_precision("fp32")

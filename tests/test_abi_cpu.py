@@ -110,6 +110,40 @@ def test_same_seed_gives_reference_init_order():
         assert abs(float(v.double().sum()) - fp["sums"][k]) <= 1e-9 + 1e-12 * abs(fp["sums"][k]), k
 
 
+def test_default_precision_is_the_reference_gpu_arithmetic():
+    from vqvae_b200 import modules
+    assert modules.DEFAULT_PRECISION == "tf32"
+    import vqvae_b200
+    for name in ("fp32", "tf32", "bf16"):
+        with vqvae_b200.precision(name):
+            assert vqvae_b200.get_precision() == name
+    with pytest.raises(ValueError):
+        vqvae_b200.set_precision("fp8")
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """bf16 pipeline entry points: bad arguments / unsupported shapes are rejected before any CUDA call."""
+    from vqvae_b200 import _lib
+    lib = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.vqb_conv2d_bf16(None, None, None, None, 1, 64, 8, 8, 64, _lib.CONV_K3, 0, 0, None) == -1
+    assert lib.vqb_conv2d_bf16(p, p, None, p, 1, 48, 8, 8, 64, _lib.CONV_K3, 0, 0, None) == -2          # Cin % 64
+    assert lib.vqb_conv2d_bf16(p, p, None, p, 1, 64, 7, 8, 64, _lib.CONV_K4S2, 0, 0, None) == -2        # odd height
+    assert lib.vqb_conv_bf16_packed_bytes(_lib.CONV_K3, 128, 128) == 9 * 2 * 128 * (128 + 16) + 256
+    assert lib.vqb_conv_bf16_packed_bytes(_lib.CONV_K3, 128, 100) == 0                                  # not covered
+    assert lib.vqb_conv_bf16_packed_bytes(_lib.CONVT_K4S2, 64, 128) > 0
+    assert lib.vqb_pack_conv_weight_bf16(None, None, _lib.CONV_K3, 128, 128, None) == -1
+    assert lib.vqb_residual_layer_bf16(None, None, None, None, 1, 8, 8, 128, 32, 1, None) == -1
+    assert lib.vqb_residual_layer_bf16(p, p, p, p, 1, 8, 8, 256, 32, 1, None) in (-1, -2)               # C = 256 / r == out
+    assert lib.vqb_conv_in_bf16(None, None, None, None, 1, 32, 32, 64, 1, None) == -1
+    assert lib.vqb_vq_forward_bf16zq_f32(None, None, 1, 1, 64, None, None, None, None, None, 0, None) == -1
+    # the fp32-activation entry points refuse the bf16 enum instead of silently running TF32 (round-1 verdict)
+    assert lib.vqb_conv2d_f32(p, p, None, None, p, 1, 64, 8, 8, 64, 3, 3, 1, 1, 0, 1, 1, 0, _lib.BF16, None) == -2
+    assert lib.vqb_residual_layer_f32(p, p, p, p, p, 1, 8, 8, 32, 32, 1, _lib.BF16, None) == -2
+    assert lib.vqb_set_vq_kernel(3) == 0 and lib.vqb_set_vq_kernel(0) == 0
+
+
 def test_no_cpu_fallback():
     from models.vqvae import VQVAE
     m = VQVAE(32, 8, 1, 16, 8, 0.25)

@@ -471,10 +471,12 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                     int sk = -1;
                     for (int k = ft; k < p.K; k += 128) {
                         float M = 0.f;
-                        const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);     // (L2; rare path)
+                        const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);     // streamed codebooks: through L2
+                        const unsigned char *es = code_ptr_smem(k);                                     // resident: shared memory
 #pragma unroll
                         for (int c16 = 0; c16 < 16; ++c16) {
-                            const float4 e = __ldg(er + c16);
+                            const float4 e = resident ? *reinterpret_cast<const float4 *>(es + (c16 >> 3) * EATOM + (((c16 & 7) ^ (k & 7)) << 4))
+                                                      : __ldg(er + c16);
                             const float4 v = *reinterpret_cast<const float4 *>(qz + (c16 >> 3) * ZATOM + (((c16 & 7) ^ (qrow & 7)) << 4));
                             M = __fmaf_rn(v.x, e.x, M); M = __fmaf_rn(v.y, e.y, M); M = __fmaf_rn(v.z, e.z, M); M = __fmaf_rn(v.w, e.w, M);
                         }

@@ -27,12 +27,19 @@ from .dist import reduce_vq_stats
 from ._lib import (CONV_K1, CONV_K3, CONV_K4S2, CONVT_K3, CONVT_K4S2, CONVT_K4S2_OUT, NCHW, NHWC, PRECISIONS,
                    RES_W2)
 
-_PRECISION = {"value": "fp32"}
+# Default = what the reference itself computes on a GPU: fp32 tensors, convolutions on tensor cores in TF32 with fp32
+# accumulation (PyTorch's torch.backends.cudnn.allow_tf32 default), bit-exact fp32 VQ.
+DEFAULT_PRECISION = "tf32"
+_PRECISION = {"value": DEFAULT_PRECISION}
 
 
 def set_precision(name: str):
-    """Arithmetic of the convolution layers: "fp32" (FFMA, the reference's CPU numerics;
-    default), "tf32" or "bf16" (tcgen05 tensor cores, fp32 accumulation)."""
+    """Arithmetic of the convolution layers:
+    "tf32" (default) tcgen05 kind::tf32 on fp32 activations, fp32 accumulation -- the reference's GPU arithmetic;
+    "fp32"  FFMA on CUDA cores -- the reference's CPU numerics (end-to-end indices equal the CPU reference);
+    "bf16"  bf16 activations and operands between layers (tcgen05 kind::f16), fp32 accumulation -- the arithmetic the
+            reference reaches through torch.autocast(dtype=torch.bfloat16); fastest.
+    The VQ distances / argmin are bit-exact fp32 in every mode."""
     if name not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
     _PRECISION["value"] = name
