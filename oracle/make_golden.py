@@ -106,6 +106,42 @@ np.savez(job["out"], **out)
 """
 
 
+_CKPT_SCRIPT = r"""
+# writes a checkpoint exactly as utils.save_model_and_results does (utils.py:106-115) from the unmodified reference model
+import sys, json, numpy as np, torch
+sys.path.insert(0, %(ref)r)
+import models.quantizer as Q
+Q.device = torch.device("cpu")
+from models.vqvae import VQVAE
+job = json.load(open(sys.argv[1]))
+data = np.load(job["in"])
+hp = job["hp"]
+m = VQVAE(hp["h_dim"], hp["res_h_dim"], hp["n_res_layers"], hp["n_embeddings"], hp["embedding_dim"], 0.25)
+m.load_state_dict({k: torch.from_numpy(data[k]) for k in m.state_dict().keys()})
+results = {"n_updates": 3, "recon_errors": [np.float32(0.5), np.float32(0.4)], "loss_vals": [np.float32(0.9), np.float32(0.8)],
+           "perplexities": [np.float32(3.0), np.float32(4.0)]}                     # main.py:59-64, 81-84
+hyper = {"batch_size": 32, "n_updates": 5000, "n_hiddens": hp["h_dim"], "n_residual_hiddens": hp["res_h_dim"],
+         "n_residual_layers": hp["n_res_layers"], "embedding_dim": hp["embedding_dim"], "n_embeddings": hp["n_embeddings"],
+         "beta": 0.25, "learning_rate": 3e-4, "log_interval": 50, "dataset": "CIFAR10", "save": True, "filename": "golden"}   # vars(args), main.py:9-32
+torch.save({"model": m.state_dict(), "results": results, "hyperparameters": hyper}, job["ckpt"])
+"""
+
+
+def make_checkpoint(name="small_odd"):
+    """tests/golden/ckpt_<name>.pth: the reference's own checkpoint format holding the weights of golden case <name>."""
+    c = MODEL_CASES[name]
+    hp = {k: c[k] for k in ("h_dim", "res_h_dim", "n_res_layers", "n_embeddings", "embedding_dim")}
+    sd = make_state_dict(seed=c["wseed"], codebook=c["codebook"], codebook_scale=c["codebook_scale"], **hp)
+    with tempfile.TemporaryDirectory() as td:
+        job = {"in": os.path.join(td, "in.npz"), "hp": hp, "ckpt": os.path.join(OUT, f"ckpt_{name}.pth")}
+        np.savez(job["in"], **sd)
+        with open(os.path.join(td, "job.json"), "w") as f:
+            json.dump(job, f)
+        subprocess.run([sys.executable, "-c", _CKPT_SCRIPT % dict(ref=REF), os.path.join(td, "job.json")], check=True, cwd=REF,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    return job["ckpt"]
+
+
 def make_vq_inputs(K, D, B, H, W, seed, kind, hash_zq=False):
     """(z NCHW, codebook) for a VectorQuantizer-only case; shared with the tests."""
     rng = np.random.RandomState(seed)
@@ -143,6 +179,8 @@ def main():
     assert os.path.isdir(REF), "needs the reference checkout (authoring container only)"
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])          # optional: regenerate just the named cases
+    if not only or "ckpt" in only:
+        print("checkpoint", make_checkpoint("small_odd"))
     for name, c in MODEL_CASES.items():
         if only and name not in only:
             continue

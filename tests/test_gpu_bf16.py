@@ -150,3 +150,21 @@ def test_bf16_model_forward_tolerance(name):
     np.testing.assert_allclose(loss.item(), 1.25 * o["sse"] / z_rows.size, rtol=1e-5)
     if flips == 0.0:
         np.testing.assert_allclose(x_hat.cpu().numpy(), g["x_hat"], atol=3e-3, rtol=0)
+
+
+@pytest.mark.parametrize("B,H,W,relu", [(2, 256, 256, True), (5, 32, 32, True), (3, 64, 64, False), (2, 16, 16, True), (1, 12, 20, True), (300, 32, 32, True)])
+def test_bf16_input_conv_vs_oracle(B, H, W, relu):
+    """encoder.py:29-31 in the bf16 pipeline: fp32 NCHW image -> bf16 NHWC.  The 48-tap contraction runs as kind::tf32 on the
+    fp32 pixels (operands truncated to 10-bit mantissas), the result is rounded once to bf16."""
+    from vqvae_b200 import ops
+    rng = np.random.RandomState(B + H)
+    x = (2 * rng.random_sample((B, 3, H, W)) - 1).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 4, 4)) / 7).astype(np.float32)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    ref = cref.conv2d(x, w, b, 2, 1)
+    if relu:
+        ref = np.maximum(ref, 0)
+    y = ops.conv_in_bf16(torch.from_numpy(x).cuda(), ops.pack_conv_weight(torch.from_numpy(w).cuda(), False), torch.from_numpy(b).cuda(),
+                         B=B, H=H, W=W, Cout=64, relu=relu)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.float().cpu().numpy().transpose(0, 3, 1, 2), ref, atol=6e-3, rtol=2.0 ** -7)

@@ -365,3 +365,20 @@ def test_fused_residual_stack_tc(B, H, W, C, Cmid, n):
         if prec == TF32 and W <= 8 and H <= 16:
             assert launches == 1, launches          # the fused path really ran
     assert torch.equal(rn.cpu(), torch.from_numpy(np.ascontiguousarray(r.transpose(0, 2, 3, 1))))   # input untouched
+
+
+def test_checkpoint_load_packs_weights_and_reproduces_the_golden_forward():
+    """a checkpoint in the reference's own format -> load_checkpoint -> forward equals the golden outputs of
+    the unmodified reference for the same weights; the weight packings exist before the first forward."""
+    import os
+    import vqvae_b200
+    g = load_golden("small_odd")
+    hp, sd, x = model_case_inputs(g["case"])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ckpt_small_odd.pth")
+    m, data = vqvae_b200.load_checkpoint(path, device="cuda")
+    w = m.encoder.conv_stack[2].weight
+    assert getattr(w, "_vqb_packed", None), "conv weights must be packed at load time"
+    loss, x_hat, perp = m(_cuda(x))
+    assert np.array_equal(m.last_min_encoding_indices.cpu().numpy(), g["idx"])
+    np.testing.assert_allclose(x_hat.cpu().numpy(), g["x_hat"], atol=CONV_ATOL, rtol=0)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)

@@ -7,7 +7,8 @@ top-level ``models`` package so ``from models.vqvae import VQVAE`` drops in).
 from .modules import (Decoder, Encoder, ResidualLayer, ResidualStack, VectorQuantizer, VQVAE,  # noqa: F401
                       get_precision, invalidate_packed, packed_state, precision, set_precision)
 from .pipeline import HostPipeline, HostResult  # noqa: F401
+from .checkpoint import load_checkpoint, save_checkpoint  # noqa: F401
 
 __all__ = ["VQVAE", "VectorQuantizer", "Encoder", "Decoder", "ResidualLayer", "ResidualStack",
            "set_precision", "get_precision", "precision", "invalidate_packed", "packed_state", "HostPipeline",
-           "HostResult"]
+           "HostResult", "load_checkpoint", "save_checkpoint"]

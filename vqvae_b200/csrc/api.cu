@@ -16,6 +16,9 @@ int launch_vq_tc(const float *z, const float *E, long long N, int K, int D, long
 int launch_conv_in_tc_ex(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int Cout,
                          int relu, int out_bf16, cudaStream_t s);
 
+bool conv_in_bf16_persistent_ok(int H, int W, const void *x);
+int launch_conv_in_bf16_persistent(const float *x, const float *wp, const float *bias, void *y, int B, int H, int W, int relu,
+                                   cudaStream_t s);
 bool vq2_supported(long long N, int K, int D);
 int launch_vq2(const float *z, const float *E, long long N, int K, int D, long long *idx, void *zq, double *sse, int *hist,
                void *ws, int defer, int zq_bf16, cudaStream_t s);
@@ -301,6 +304,10 @@ extern "C" int vqb_conv_in_bf16(const float *x, const float *w_packed, const flo
     if (!x || !w_packed || !out) return VQB_ERR_BAD_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return VQB_ERR_BAD_ARG;
     if (!conv_in_tc_supported(3, Cout, H, W, out) || Cout != 64) return VQB_ERR_UNSUPPORTED;
+    if (conv_in_bf16_persistent_ok(H, W, x)) {          // one CTA per SM, pipelined over tiles (conv_in_bf16.cu)
+        const int rc = launch_conv_in_bf16_persistent(x, w_packed, bias, out, B, H, W, relu, (cudaStream_t)stream);
+        if (rc != VQB_ERR_UNSUPPORTED) return rc;
+    }
     return launch_conv_in_tc_ex(x, w_packed, bias, out, B, H, W, Cout, relu, 1, (cudaStream_t)stream);
 }
 
