@@ -211,6 +211,16 @@ int vqb_debug_vq_scores_f32(const float *z, const float *codebook, int64_t N, in
                             void *workspace, size_t workspace_bytes, float *scores,
                             void *stream);
 
+/* ---- backward of VectorQuantizer.forward, quantizer.py:63-67 (training-mode callers, main.py:74-79) ----
+ * g_zq (N,D) = gradient arriving at the returned z_q (straight-through: passes to z unchanged), g_loss = device
+ * scalar gradient of the returned loss (either may be NULL = zero).  Writes
+ *   dz (N,D) = g_zq + g_loss * 2/(N D) * (z - E[idx])
+ *   dE (K,D) = g_loss * 2 beta/(N D) * sum_{i: idx[i]=k} (E[k] - z[i])      (zeroed, then scatter-added by index)
+ * argmin / one-hot / perplexity carry no gradient.  D % 4 == 0, 16-byte aligned pointers.                */
+int vqb_vq_backward_f32(const float *g_zq, const float *g_loss, const float *z, const float *codebook,
+                        const int64_t *idx, int64_t N, int K, int D, float beta, float *dz, float *dE,
+                        void *stream);
+
 /* loss = (1+beta)*sse/(N*D) and perplexity = exp(-sum p log(p+1e-10)), p = hist/N,
  * written as two fp32 device scalars (quantizer.py:63-64, :70-71).  Separate from
  * the VQ kernel so a batch-sharded caller can all-reduce (hist, sse) in between.  */

@@ -382,3 +382,36 @@ def test_checkpoint_load_packs_weights_and_reproduces_the_golden_forward():
     assert np.array_equal(m.last_min_encoding_indices.cpu().numpy(), g["idx"])
     np.testing.assert_allclose(x_hat.cpu().numpy(), g["x_hat"], atol=CONV_ATOL, rtol=0)
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+
+
+def test_vq_backward_matches_autograd_of_the_reference_formula():
+    """VectorQuantizer in training mode (grad enabled): loss.backward() + a downstream gradient on z_q give the
+    straight-through gradient on z and the scatter-added codebook gradient of quantizer.py:63-67 (torch autograd on CPU as oracle)."""
+    from models.quantizer import VectorQuantizer
+    rng = np.random.RandomState(3)
+    K, D = 37, 16
+    z0 = rng.standard_normal((3, D, 5, 7)).astype(np.float32)
+    E0 = rng.standard_normal((K, D)).astype(np.float32)
+    gq = rng.standard_normal((3, D, 5, 7)).astype(np.float32)
+    # reference formula with torch autograd (CPU)
+    z = torch.tensor(z0, requires_grad=True)
+    E = torch.tensor(E0, requires_grad=True)
+    zf = z.permute(0, 2, 3, 1).contiguous().view(-1, D)
+    d = (zf ** 2).sum(1, keepdim=True) + (E ** 2).sum(1) - 2 * zf @ E.t()
+    idx = d.argmin(1)
+    zq = E[idx].view(3, 5, 7, D)
+    zp = z.permute(0, 2, 3, 1)
+    loss = ((zq.detach() - zp) ** 2).mean() + 0.25 * ((zq - zp.detach()) ** 2).mean()
+    out = (zp + (zq - zp).detach()).permute(0, 3, 1, 2)
+    (loss * 1.7 + (out * torch.tensor(gq)).sum()).backward()
+    # product
+    vq = VectorQuantizer(K, D, 0.25).cuda()
+    vq.embedding.weight.data.copy_(torch.from_numpy(E0))
+    zc = torch.tensor(z0, device="cuda", requires_grad=True)
+    l2, zq2, perp2, oh2, idx2 = vq(zc)
+    assert np.array_equal(idx2.view(-1).cpu().numpy(), idx.numpy())
+    (l2 * 1.7 + (zq2 * torch.tensor(gq, device="cuda")).sum()).backward()
+    np.testing.assert_allclose(l2.item(), loss.item(), rtol=1e-6)
+    np.testing.assert_allclose(zc.grad.cpu().numpy(), z.grad.numpy(), atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(vq.embedding.weight.grad.cpu().numpy(), E.grad.numpy(), atol=1e-6, rtol=1e-5)
+    assert perp2.requires_grad is False and oh2.shape == (105, K)

@@ -353,6 +353,28 @@ class Decoder(nn.Module):
         return self._forward_from_nhwc(ops.nchw_to_nhwc(x), B, H, W)
 
 
+class _VQFunction(torch.autograd.Function):
+    """Training-mode VectorQuantizer core: the fused forward kernel plus vqb_vq_backward_f32 --
+    straight-through gradient to z, commitment / codebook gradients scatter-added by index (quantizer.py:63-67)."""
+
+    @staticmethod
+    def forward(ctx, z_rows, codebook, beta):
+        z_rows, codebook = z_rows.detach().contiguous(), codebook.detach().contiguous()
+        idx, zq, sse, hist = ops.vq_forward(z_rows, codebook)
+        N, D = z_rows.shape
+        loss, perp = ops.vq_finish(sse, hist, N, codebook.shape[0], D, beta)
+        ctx.save_for_backward(z_rows, codebook, idx)
+        ctx.beta = beta
+        ctx.mark_non_differentiable(perp, idx)
+        return loss, zq, perp, idx
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, _g_perp, _g_idx):
+        z_rows, codebook, idx = ctx.saved_tensors
+        dz, dE = ops.vq_backward(g_zq, g_loss, z_rows, codebook, idx, ctx.beta)
+        return dz, dE, None
+
+
 class VectorQuantizer(nn.Module):
     """Discretisation bottleneck: models/quantizer.py:10-76."""
 
@@ -388,7 +410,21 @@ class VectorQuantizer(nn.Module):
         loss, perp = self._scalars(sse, hist, rows.shape[0], group)
         return loss, zq, perp, idx
 
+    def _forward_train(self, z):
+        """Differentiable path (z or the codebook requires grad): same kernels, gradients through _VQFunction; the
+        NCHW <-> row layout changes are plain torch views/copies so autograd carries them."""
+        if z.dim() != 4 or z.shape[1] != self.e_dim:
+            raise RuntimeError(f"VectorQuantizer: expected (B,{self.e_dim},H,W), got {tuple(z.shape)}")
+        ops._require_cuda(z, "VectorQuantizer input")
+        B, D, H, W = z.shape
+        rows = z.float().permute(0, 2, 3, 1).contiguous().view(-1, D)                   # quantizer.py:45-46
+        loss, zq, perp, idx = _VQFunction.apply(rows, self.embedding.weight.float(), float(self.beta))
+        z_q = zq.view(B, H, W, D).permute(0, 3, 1, 2).contiguous()                      # :74
+        return loss, z_q, perp, ops.onehot(idx, self.n_e), idx.view(-1, 1)
+
     def forward(self, z):
+        if torch.is_grad_enabled() and (z.requires_grad or self.embedding.weight.requires_grad) and z.is_cuda:
+            return self._forward_train(z)
         z = _prep_input(z, self.e_dim, "VectorQuantizer")   # Q11: channels must equal e_dim
         B, D, H, W = z.shape
         rows = ops.nchw_to_nhwc(z).view(-1, D)                              # quantizer.py:45-46

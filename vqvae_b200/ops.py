@@ -264,6 +264,21 @@ def vq_finish(sse, hist, N, K, D, beta):
     return out[0], out[1]
 
 
+def vq_backward(g_zq, g_loss, z_rows, codebook, idx, beta):
+    """(dz (N,D), dE (K,D)) of the VectorQuantizer forward (vqb_vq_backward_f32); g_zq / g_loss may be None."""
+    _require_cuda(z_rows, "z")
+    N, D = z_rows.shape
+    K = codebook.shape[0]
+    dz = torch.empty_like(z_rows)
+    dE = torch.empty((K, D), dtype=torch.float32, device=z_rows.device)
+    gz = _f32c(g_zq) if g_zq is not None else None
+    gl = _f32c(g_loss).reshape(1) if g_loss is not None else None
+    check(lib().vqb_vq_backward_f32(gz.data_ptr() if gz is not None else None, gl.data_ptr() if gl is not None else None,
+                                    z_rows.data_ptr(), codebook.data_ptr(), idx.data_ptr(), N, K, D, float(beta),
+                                    dz.data_ptr(), dE.data_ptr(), _stream()), "vq_backward")
+    return dz, dE
+
+
 def onehot(idx, K):
     N = idx.numel()
     out = torch.empty((N, K), dtype=torch.float32, device=idx.device)
