@@ -15,6 +15,10 @@ from tests.helpers import (MODEL_CASES, VQ_CASES, assert_zq_matches, build_model
 
 pytestmark = pytest.mark.gpu
 
+# The tcgen05 VQ kernel sums (e - z)^2 of one row in four fp32 partials (64 terms) and adds rows in double; the FFMA kernel and
+# the oracle add every term in double.  Per-row relative error <= 16 * 2^-24 ~ 1e-6, random in sign across rows.
+SSE_RTOL = 2e-6
+
 CONV_ATOL = 2e-6     # fp32 FFMA vs double-accumulated oracle, activations O(0.1..1)
 
 
@@ -40,7 +44,7 @@ def test_vq_kernel_bit_exact_vs_oracle_and_reference(name):
     assert np.array_equal(zq.cpu().numpy(), o["zq"], equal_nan=True)         # bitwise vs oracle
     assert_zq_matches(g, zq.cpu().numpy().reshape(B, H, W, D).transpose(0, 3, 1, 2))   # bitwise vs reference
     assert np.array_equal(hist.cpu().numpy(), g["hist"])
-    np.testing.assert_allclose(sse.item(), o["sse"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(sse.item(), o["sse"], rtol=SSE_RTOL, equal_nan=True)
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-6, equal_nan=True)
     np.testing.assert_allclose(perp.item(), g["perplexity"], rtol=2e-5)
 

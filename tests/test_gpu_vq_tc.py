@@ -8,6 +8,10 @@ from oracle import cref
 
 pytestmark = pytest.mark.gpu
 
+# The tcgen05 VQ kernel sums (e - z)^2 of one row in four fp32 partials (64 terms) and adds rows in double; the FFMA kernel and
+# the oracle add every term in double.  Per-row relative error <= 16 * 2^-24 ~ 1e-6, random in sign across rows.
+SSE_RTOL = 2e-6
+
 
 def _cuda(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
@@ -82,7 +86,7 @@ def test_tc_kernel_bit_exact_vs_exact_kernel_and_oracle(N, K, kind):
     assert np.array_equal(i_t, o["idx"]), int((i_t != o["idx"]).sum())
     assert np.array_equal(q_t, o["zq"], equal_nan=True)
     assert np.array_equal(h_t, o["hist"])
-    np.testing.assert_allclose(s_t, s_e, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(s_t, s_e, rtol=SSE_RTOL, equal_nan=True)
 
 
 @pytest.mark.parametrize("K,kind", [(512, "normal"), (512, "default"), (1024, "normal")])
@@ -95,7 +99,7 @@ def test_tc_kernel_large_n_matches_exact_kernel(K, kind):
     assert np.array_equal(i_t, i_e), int((i_t != i_e).sum())
     assert np.array_equal(q_t, q_e)
     assert np.array_equal(h_t, h_e) and int(h_t.sum()) == 1 << 18
-    np.testing.assert_allclose(s_t, s_e, rtol=1e-12)
+    np.testing.assert_allclose(s_t, s_e, rtol=SSE_RTOL)
     # oracle spot check on a slice
     o = cref.vq_rows(z[:4096], E)
     assert np.array_equal(i_t[:4096], o["idx"])

@@ -26,6 +26,7 @@ constexpr int CIB_THREADS = 512;
 constexpr int COUT = 64;
 constexpr uint32_t A_BYTES = 2 * 16384;                 // two K atoms x [128 rows][128 B]
 constexpr uint32_t B_ATOM = COUT * 128;
+constexpr int NRAW = 4;                                 // staged-input buffers: the TMA loads run three tiles ahead (HBM round trip)
 
 struct CibParams {
     const float *wp, *bias;
@@ -50,23 +51,23 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     // [A x2][B: 2 atoms][staging 16 KB][raw rows x2][barriers, bias]
     const uint32_t b_off = 2 * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + 16384u;
     const uint32_t raw_stride = ((uint32_t)p.raw_bytes + 127u) & ~127u;
-    const uint32_t bar_off = raw_off + 2 * raw_stride;
+    const uint32_t bar_off = raw_off + NRAW * raw_stride;
     const uint32_t bars = sbase + bar_off;
     auto rfull = [&](int s) { return bars + 8u * s; };
-    auto rempty = [&](int s) { return bars + 8u * (2 + s); };
-    auto afull = [&](int s) { return bars + 8u * (4 + s); };
-    auto aempty = [&](int s) { return bars + 8u * (6 + s); };
-    auto tfull = [&](int s) { return bars + 8u * (8 + s); };
-    auto tempty = [&](int s) { return bars + 8u * (10 + s); };
-    const uint32_t sfree = bars + 8u * 12;
-    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 112);
-    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 128);
+    auto rempty = [&](int s) { return bars + 8u * (NRAW + s); };
+    auto afull = [&](int s) { return bars + 8u * (2 * NRAW + s); };
+    auto aempty = [&](int s) { return bars + 8u * (2 * NRAW + 2 + s); };
+    auto tfull = [&](int s) { return bars + 8u * (2 * NRAW + 4 + s); };
+    auto tempty = [&](int s) { return bars + 8u * (2 * NRAW + 6 + s); };
+    const uint32_t sfree = bars + 8u * (2 * NRAW + 8);
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 10));
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 12));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, W = p.W, OW = W / 2, OH = H / 2, R = p.R, NR = 2 * R + 2;
     if (tid == 0) {
+        for (int s = 0; s < NRAW; ++s) { ptx::mbar_init(rfull(s), 1); ptx::mbar_init(rempty(s), 8); }
         for (int s = 0; s < 2; ++s) {
-            ptx::mbar_init(rfull(s), 1); ptx::mbar_init(rempty(s), 8);
             ptx::mbar_init(afull(s), 8); ptx::mbar_init(aempty(s), 1);
             ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4);
         }
@@ -74,7 +75,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tma_x); ptx::prefetch_tmap(&tma_out);
     }
-    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 112, 128);
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * NRAW + 10), 128);
     for (int c = tid; c < COUT; c += CIB_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
     // ---- B operand, once per CTA: wp[k][co] (k = (r*4+s)*3 + c, 48 rows) -> K-major swizzled rows ----
     for (int i = tid; i < COUT * 12; i += CIB_THREADS) {
@@ -99,13 +100,13 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         // ===================== TMA producer: input rows =====================
         if (ptx::elect_one()) {
             pdl_wait();
-            int it = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-                const int s = it & 1;
+            uint32_t rs = 0, rpar = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
                 const int n = (int)(tile / tiles_per_img), oy0 = (int)(tile % tiles_per_img) * R;
-                ptx::mbar_wait(rempty(s), (uint32_t)(((it >> 1) & 1) ^ 1));
-                ptx::mbar_expect_tx(rfull(s), (uint32_t)p.raw_bytes);
-                tma_load_4d_nosw(sbase + raw_off + s * raw_stride, &tma_x, rfull(s), 0, 2 * oy0 - 1, 0, n);
+                ptx::mbar_wait_sleep(rempty((int)rs), rpar ^ 1, 100);
+                ptx::mbar_expect_tx(rfull((int)rs), (uint32_t)p.raw_bytes);
+                tma_load_4d_nosw(sbase + raw_off + rs * raw_stride, &tma_x, rfull((int)rs), 0, 2 * oy0 - 1, 0, n);
+                if (++rs == NRAW) { rs = 0; rpar ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -132,11 +133,12 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         const int row = bt & 127, hf = bt >> 7;
         const int r = row >> p.log2_ow, ox = row & (OW - 1);
         int it = 0;
+        uint32_t rs = 0, rpar = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             const int s = it & 1;
-            ptx::mbar_wait(rfull(s), (uint32_t)((it >> 1) & 1));
-            ptx::mbar_wait(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1));
-            const float *rawp = reinterpret_cast<const float *>(sm + raw_off + s * raw_stride);
+            ptx::mbar_wait_sleep(rfull((int)rs), rpar, 100);
+            ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1), 100);
+            const float *rawp = reinterpret_cast<const float *>(sm + raw_off + rs * raw_stride);
             float v[24];                                          // k_local = (trl*4 + s)*3 + c
 #pragma unroll
             for (int trl = 0; trl < 2; ++trl)
@@ -150,7 +152,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                     v[(trl * 4 + 3) * 3 + c] = ox < OW - 1 ? b[2] : 0.f;
                 }
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(rempty(s));           // the staged rows may be overwritten
+            if (lane == 0) ptx::mbar_arrive(rempty((int)rs));     // the staged rows may be overwritten
+            if (++rs == NRAW) { rs = 0; rpar ^= 1; }
             unsigned char *arow = sm + s * A_BYTES + row * 128;
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
@@ -170,7 +173,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             const int s = it & 1;
-            ptx::mbar_wait(tfull(s), (uint32_t)((it >> 1) & 1));
+            ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it >> 1) & 1), 100);
             ptx::tc_fence_after();
             float va[32], vb[32];
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * COUT);
@@ -248,7 +251,7 @@ int launch_conv_in_bf16_persistent(const float *x, const float *wp, const float 
         if (rc) return rc;
     }
     const int raw_stride = (q.raw_bytes + 127) & ~127;
-    const int smem = 2 * (int)A_BYTES + 2 * (int)B_ATOM + 16384 + 2 * raw_stride + 128 + COUT * 4 + 1024;
+    const int smem = 2 * (int)A_BYTES + 2 * (int)B_ATOM + 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 12) + COUT * 4 + 1024;
     if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
     static int attr_max = 0;
     if (smem > attr_max) {

@@ -43,17 +43,19 @@ constexpr int HC_MAX_STAGES = 40;
 constexpr int HC_MAX_CHUNKS = 8;
 constexpr int HC_MAX_HB = 3;
 
-enum { ST_FIRST = 1, ST_NEWCHUNK = 2, ST_ENDCHUNK = 4, ST_HALFBOX = 8 };
+enum { ST_FIRST = 1, ST_NEWCHUNK = 2, ST_ENDCHUNK = 4, ST_HALFBOX = 8, ST_GSTART = 16, ST_GEND = 32 };
 enum { EPI_NHWC = 0, EPI_SHUFFLE_NCHW = 1 };
 
-struct HStep {
-    uint32_t a_off16;      // tap offset inside the halo tile, 16-byte units (M-tile 0)
-    uint16_t w_row;        // first row of this step's weight tile in the packed matrix
-    uint8_t nb8;           // MMA N / 8
-    uint8_t d_col;         // accumulator column offset inside the M-tile's column block
-    uint8_t flags;
-    uint8_t pad[3];
-};
+// One k-step (tap x 64-channel chunk), 16 bytes, copied to shared memory at kernel start so that the single-warp issue
+// loops read it with one LDS.128 (the first version indexed the kernel parameters: ~150 dependent scalar instructions
+// and ~1100 cycles per step whatever the MMA shape -- every layer ran at the same 0.55-0.6 us per step).
+//   x: tap offset inside the halo tile, 16-byte units (M-tile 0)         y: UMMA instruction descriptor (N of this step)
+//   z: [0,8) accumulator column offset  [8,20) offset of the weight tile inside its ring stage / 16  [20,32) bytes of the
+//      whole stage group / 16 (valid on the group's first step)
+//   w: [0,8) flags  [8,24) first row of the weight tile in the packed matrix  [24,32) N / 8
+// Weight tiles travel in GROUPS of consecutive steps (<= 32 KB, <= 4 steps) sharing one ring stage and one full / empty
+// barrier pair: one mbarrier wait and one tcgen05.commit per 16 MMAs instead of per 8.
+struct HStep { uint32_t x, y, z, w; };
 
 struct HParams {
     const float *bias;
@@ -65,11 +67,18 @@ struct HParams {
     int NCOL;                       // accumulator columns per M-tile
     int nsteps[2], nchunks;
     int chunk_c0[HC_MAX_CHUNKS], chunk_p[HC_MAX_CHUNKS];
-    int S, wst_bytes, resident, nhb, halo_bytes, halo_stride;
+    int S, wst_bytes, resident, nhb, halo_bytes, halo_stride;     // S ring stages of wst_bytes (= largest step group)
     int epi_mode, cg, sy, sx, OH, OW, Cout, relu, out_f32, bias_mod;
+    int res_groups0;                // resident mode: number of step groups (= ring stages) of pass 0
     HStep steps[2][HC_MAX_STEPS];
 };
 
+__device__ __forceinline__ void prefetch_l2_5d(const CUtensorMap *m, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::
+                     "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int MT>
 __global__ void __launch_bounds__(HC_THREADS, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
              const __grid_constant__ CUtensorMap tma_wh, const __grid_constant__ HParams p) {
@@ -90,6 +99,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
     constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + MISC);
     float *bias_s = reinterpret_cast<float *>(sm + bar_off + MISC + 16);
+    uint4 *steps_s = reinterpret_cast<uint4 *>(sm + bar_off + MISC + 16 + 256 * 4);        // [2][HC_MAX_STEPS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -106,6 +116,10 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         }
         bias_s[c] = b;
     }
+    for (int i = tid; i < 2 * HC_MAX_STEPS; i += HC_THREADS) {
+        const HStep st = p.steps[i / HC_MAX_STEPS][i % HC_MAX_STEPS];
+        steps_s[i] = make_uint4(st.x, st.y, st.z, st.w);
+    }
     if (warp == 2) ptx::tmem_alloc(sbase + bar_off + MISC, 512);
     ptx::tc_fence_before();
     __syncthreads();
@@ -121,13 +135,25 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         const bool leader = ptx::elect_one();
         pdl_wait();                                  // the input activation is the previous layer's output
         uint32_t hb = 0, hpar = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+        auto tile_origin = [&](long long tile, int &gx0, int &gy0, int &n0) {
             long long t = tile / p.npass;
             const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
-            const int gx0 = tx * p.TW, gy0 = ty * p.BH, n0 = (int)t * p.BN;
+            gx0 = tx * p.TW; gy0 = ty * p.BH; n0 = (int)t * p.BN;
+        };
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+            int gx0, gy0, n0;
+            tile_origin(tile, gx0, gy0, n0);
+            // pull the halo tiles of the tile after next into L2 now: with <= 3 halo buffers the shared-memory load of a
+            // tile can only be issued one tile ahead, which does not cover an HBM round trip under full load
+            const long long tpf = tile + 2LL * G;
+            if (leader && tpf < ntiles && (p.npass == 1 || (tpf % p.npass) == 0)) {
+                int px0, py0, pn0;
+                tile_origin(tpf, px0, py0, pn0);
+                for (int k = 0; k < p.nchunks; ++k) prefetch_l2_5d(&tma_in, p.chunk_c0[k], px0 - p.halo, pn0, p.chunk_p[k], py0 - p.halo);
+            }
             for (int k = 0; k < p.nchunks; ++k) {
-                ptx::mbar_wait(hempty((int)hb), hpar ^ 1);
+                ptx::mbar_wait_sleep(hempty((int)hb), hpar ^ 1, 100);
                 if (leader) {
                     ptx::mbar_expect_tx(hfull((int)hb), (uint32_t)p.halo_bytes);
                     tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), p.chunk_c0[k], gx0 - p.halo, n0,
@@ -137,32 +163,33 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             }
         }
     } else if (warp == 3) {
-        // ===================== weight producer =====================
+        // ===================== weight producer: one ring stage (and one barrier) per step GROUP =====================
         const bool leader = ptx::elect_one();
+        auto load_group = [&](const uint4 *sp, int i, int ns, uint32_t stage) -> int {       // returns the index after the group
+            const uint32_t gbytes = ((sp[i].z >> 20) & 0xfffu) << 4;
+            if (leader) ptx::mbar_expect_tx(wfull((int)stage), gbytes);
+            for (;; ++i) {
+                const uint4 st = sp[i];
+                if (leader)
+                    ptx::tma_load_2d(sbase + ring_off + stage * (uint32_t)p.wst_bytes + (((st.z >> 8) & 0xfffu) << 4),
+                                     (st.w & ST_HALFBOX) ? &tma_wh : &tma_w, wfull((int)stage), 0, (int)((st.w >> 8) & 0xffffu));
+                if (st.w & ST_GEND) break;
+            }
+            (void)ns;
+            return i + 1;
+        };
         if (p.resident) {
-            int s = 0;
+            uint32_t stage = 0;
             for (int ps = 0; ps < p.npass; ++ps)
-                for (int i = 0; i < p.nsteps[ps]; ++i, ++s) {
-                    const HStep st = p.steps[ps][i];
-                    if (leader) {
-                        ptx::mbar_expect_tx(wfull(s), (uint32_t)st.nb8 * 8u * 128u);
-                        ptx::tma_load_2d(sbase + ring_off + (uint32_t)(s * p.wst_bytes), (st.flags & ST_HALFBOX) ? &tma_wh : &tma_w,
-                                         wfull(s), 0, (int)st.w_row);
-                    }
-                }
+                for (int i = 0; i < p.nsteps[ps]; ++stage) i = load_group(steps_s + ps * HC_MAX_STEPS, i, p.nsteps[ps], stage);
         } else {
             uint32_t ws = 0, wpar = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
                 const int ps = (int)(tile % p.npass);
                 const int ns = p.nsteps[ps];
-                for (int i = 0; i < ns; ++i) {
-                    const HStep st = p.steps[ps][i];
-                    ptx::mbar_wait(wempty((int)ws), wpar ^ 1);
-                    if (leader) {
-                        ptx::mbar_expect_tx(wfull((int)ws), (uint32_t)st.nb8 * 8u * 128u);
-                        ptx::tma_load_2d(sbase + ring_off + ws * (uint32_t)p.wst_bytes, (st.flags & ST_HALFBOX) ? &tma_wh : &tma_w,
-                                         wfull((int)ws), 0, (int)st.w_row);
-                    }
+                for (int i = 0; i < ns;) {
+                    ptx::mbar_wait_sleep(wempty((int)ws), wpar ^ 1, 64);
+                    i = load_group(steps_s + ps * HC_MAX_STEPS, i, ns, ws);
                     if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
                 }
             }
@@ -173,50 +200,56 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         const uint32_t a_hi = ptx::desc_hi_sw128((uint32_t)(p.WP * 128)), b_hi = ptx::desc_hi_sw128(1024);
         const uint32_t ring16 = (sbase + ring_off) >> 4, wst16 = (uint32_t)p.wst_bytes >> 4;
         const uint32_t halo16 = sbase >> 4, hstride16 = (uint32_t)p.halo_stride >> 4;
+        const uint32_t ncol = (uint32_t)p.NCOL;
+        const bool resident = p.resident != 0;
         uint32_t hb = 0, hpar = 0, ws = 0, wpar = 0;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             const int ps = (int)(tile % p.npass);
             const int ns = p.nsteps[ps];
             const int acc = it & 1;
+            const uint4 *sp = steps_s + ps * HC_MAX_STEPS;
+            uint4 st = sp[0];
             ptx::mbar_wait(tempty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
-            ptx::tc_fence_after();
             const uint32_t dbase = tmem_base + (uint32_t)(acc * 256);
-            int sres = ps == 0 ? 0 : p.nsteps[0];            // resident mode: stage = global step index
+            if (resident) ws = ps == 0 ? 0u : (uint32_t)p.res_groups0;          // stage = group index over both passes
             for (int i = 0; i < ns; ++i) {
-                const HStep st = p.steps[ps][i];
-                if (st.flags & ST_NEWCHUNK) ptx::mbar_wait(hfull((int)hb), hpar);
-                uint32_t stage;
-                if (p.resident) {
-                    stage = (uint32_t)(sres + i);
-                    if (it < 2) ptx::mbar_wait(wfull((int)stage), 0);            // each pass first occurs at it <= 1
-                } else {
-                    stage = ws;
-                    ptx::mbar_wait(wfull((int)ws), wpar);
+                const uint4 nx = sp[i + 1];                                       // (one entry of slack behind the table)
+                const uint32_t fl = st.w;
+                if (fl & ST_NEWCHUNK) ptx::mbar_wait(hfull((int)hb), hpar);
+                if (fl & ST_GSTART) {
+                    if (!resident) ptx::mbar_wait(wfull((int)ws), wpar);
+                    else if (it < 2) ptx::mbar_wait(wfull((int)ws), 0);          // each pass first occurs at it <= 1
                 }
                 ptx::tc_fence_after();
-                const uint32_t idesc = ptx::instr_desc(ptx::FMT_BF16, 128, (uint32_t)st.nb8 * 8u);
-                const uint32_t a_lo = halo16 + hb * hstride16 + st.a_off16;
-                const uint32_t b_lo = ring16 + stage * wst16;
-                const uint32_t d0 = dbase + (uint32_t)st.d_col;
-                uint32_t accf = (st.flags & ST_FIRST) ? 0u : 1u;
-                for (int m = 0; m < p.MT; ++m) {
-                    uint32_t af = accf;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (leader) mma_bf16_w(d0 + (uint32_t)(m * p.NCOL), a_lo + (uint32_t)(m * 64) + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, af);
-                        af = 1u;
+                const uint32_t a_lo = halo16 + hb * hstride16 + st.x;
+                const uint32_t b_lo = ring16 + ws * wst16 + ((st.z >> 8) & 0xfffu);
+                const uint32_t d0 = dbase + (st.z & 0xffu);
+                const uint32_t idesc = st.y;
+                const uint32_t accf = (fl & ST_FIRST) ? 0u : 1u;
+                if (leader) {
+                    mma_bf16_w(d0, a_lo, a_hi, b_lo, b_hi, idesc, accf);
+                    mma_bf16_w(d0, a_lo + 2u, a_hi, b_lo + 2u, b_hi, idesc, 1u);
+                    mma_bf16_w(d0, a_lo + 4u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
+                    mma_bf16_w(d0, a_lo + 6u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
+                    if (MT == 2) {
+                        mma_bf16_w(d0 + ncol, a_lo + 64u, a_hi, b_lo, b_hi, idesc, accf);
+                        mma_bf16_w(d0 + ncol, a_lo + 66u, a_hi, b_lo + 2u, b_hi, idesc, 1u);
+                        mma_bf16_w(d0 + ncol, a_lo + 68u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
+                        mma_bf16_w(d0 + ncol, a_lo + 70u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
                     }
                 }
-                if (!p.resident) {
-                    if (leader) ptx::tc_commit(wempty((int)ws));
-                    if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                if (fl & ST_GEND) {
+                    if (!resident) {
+                        if (leader) ptx::tc_commit(wempty((int)ws));
+                        if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                    } else ++ws;
                 }
-                if (st.flags & ST_ENDCHUNK) {
+                if (fl & ST_ENDCHUNK) {
                     if (leader) ptx::tc_commit(hempty((int)hb));
                     if (++hb == (uint32_t)p.nhb) { hb = 0; hpar ^= 1; }
                 }
-                __syncwarp();
+                st = nx;
             }
             if (leader) ptx::tc_commit(tfull(acc));
             __syncwarp();
@@ -225,9 +258,9 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         // ===================== epilogue =====================
         const int q = warp & 3, g = (warp - 4) >> 2;
         const int row = q * 32 + lane;
-        const int em = p.MT == 2 ? g : 0;
-        const int ncol_thr = p.MT == 2 ? p.NCOL : (p.NCOL >= 64 ? p.NCOL / 2 : (g == 0 ? p.NCOL : 0));
-        const int c_lo = (p.MT == 2 || p.NCOL < 64) ? 0 : g * (p.NCOL / 2);
+        const int em = MT == 2 ? g : 0;
+        const int ncol_thr = MT == 2 ? p.NCOL : (p.NCOL >= 64 ? p.NCOL / 2 : (g == 0 ? p.NCOL : 0));
+        const int c_lo = (MT == 2 || p.NCOL < 64) ? 0 : g * (p.NCOL / 2);
         const int xx = row & 7, grp = row >> 3;
         const int bn = grp % p.BN, yy = grp / p.BN;
         int it = 0;
@@ -239,7 +272,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             const int gx = tx * p.TW + em * 8 + xx, gy = ty * p.BH + yy, n = (int)t * p.BN + bn;
             const bool valid = gx < p.W && gy < p.H && n < p.B;
             const int acc = it & 1;
-            ptx::mbar_wait(tfull(acc), (uint32_t)((it >> 1) & 1));
+            ptx::mbar_wait_sleep(tfull(acc), (uint32_t)((it >> 1) & 1), 200);     // (parked warps must not poll: they outrank the MMA warp)
             ptx::tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + em * p.NCOL);
             if (p.epi_mode == EPI_SHUFFLE_NCHW) {
@@ -550,28 +583,52 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
     q.NCOL = pl->NCOL;
     q.nchunks = pl->nchunks;
     for (int k = 0; k < pl->nchunks; ++k) { q.chunk_c0[k] = pl->chunk_c0[k]; q.chunk_p[k] = pl->chunk_p[k]; }
-    int total_steps = 0;
+    // ---- step table: groups of consecutive steps (<= 32 KB of weight tiles, <= 4 steps) share a ring stage ----
+    constexpr int GROUP_BYTES = 32 * 1024, GROUP_STEPS = 4;
+    int ngroups[2] = {0, 0}, max_group_bytes = 0;
+    long long total_group_bytes = 0;
     for (int ps = 0; ps < pl->npass; ++ps) {
         q.nsteps[ps] = pl->nsteps[ps];
-        total_steps += pl->nsteps[ps];
+        int gstart = 0, gbytes = 0, gcount = 0;
         for (int i = 0; i < pl->nsteps[ps]; ++i) {
             const PlanStep &a = pl->steps[ps][i];
+            const int bytes = a.nb * 128;
+            if (gcount > 0 && (gbytes + bytes > GROUP_BYTES || gcount == GROUP_STEPS)) {      // close the running group
+                q.steps[ps][gstart].z |= (uint32_t)(gbytes >> 4) << 20;
+                q.steps[ps][i - 1].w |= ST_GEND;
+                if (gbytes > max_group_bytes) max_group_bytes = gbytes;
+                total_group_bytes += gbytes; ++ngroups[ps];
+                gbytes = 0; gcount = 0;
+            }
             HStep &d = q.steps[ps][i];
-            d.a_off16 = (uint32_t)((((a.dy + q.halo) * q.BN) * q.WP + (a.dx + q.halo)) * 8);
-            d.w_row = (uint16_t)a.w_row; d.nb8 = (uint8_t)(a.nb / 8); d.d_col = (uint8_t)a.d_col; d.flags = (uint8_t)a.flags;
+            d.x = (uint32_t)((((a.dy + q.halo) * q.BN) * q.WP + (a.dx + q.halo)) * 8);
+            d.y = ptx::instr_desc(ptx::FMT_BF16, 128, (uint32_t)a.nb);
+            d.z = (uint32_t)a.d_col | ((uint32_t)(gbytes >> 4) << 8);
+            d.w = (uint32_t)a.flags | ((uint32_t)a.w_row << 8) | ((uint32_t)(a.nb / 8) << 24);
+            if (gcount == 0) { d.w |= ST_GSTART; gstart = i; }
+            gbytes += bytes; ++gcount;
+        }
+        if (gcount > 0) {
+            q.steps[ps][gstart].z |= (uint32_t)(gbytes >> 4) << 20;
+            q.steps[ps][pl->nsteps[ps] - 1].w |= ST_GEND;
+            if (gbytes > max_group_bytes) max_group_bytes = gbytes;
+            total_group_bytes += gbytes; ++ngroups[ps];
         }
     }
+    q.res_groups0 = ngroups[0];
     q.halo_bytes = (q.BH + 2 * q.halo) * q.BN * q.WP * 128;
     q.halo_stride = (q.halo_bytes + 1023) & ~1023;
-    q.wst_bytes = pl->nbmax * 128;
-    q.nhb = pl->nchunks == 1 ? 2 : HC_MAX_HB;
-    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4) + 16 + 256 * 4 + 1024;
+    q.wst_bytes = (max_group_bytes + 1023) & ~1023;
+    q.nhb = HC_MAX_HB;
+    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4) + 16 + 256 * 4 + 2 * HC_MAX_STEPS * 16 + 16 + 1024;
     int S = (227 * 1024 - q.nhb * q.halo_stride - MISC) / q.wst_bytes;
+    if (S < 2) { q.nhb = 2; S = (227 * 1024 - q.nhb * q.halo_stride - MISC) / q.wst_bytes; }
     if (S > HC_MAX_STAGES) S = HC_MAX_STAGES;
     if (S < 2) return VQB_ERR_UNSUPPORTED;
-    q.resident = total_steps <= S ? 1 : 0;
-    if (q.resident) S = total_steps;
-    else if (S > 12) S = 12;
+    const int all_groups = ngroups[0] + ngroups[1];
+    q.resident = all_groups <= S ? 1 : 0;
+    if (q.resident) S = all_groups;
+    else if (S > 6) S = 6;
     q.S = S;
     q.epi_mode = pl->epi_mode; q.cg = pl->cg; q.sy = pl->sy; q.sx = pl->sx;
     q.OH = GH * pl->sy; q.OW = GW * pl->sx;
@@ -603,17 +660,20 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
         if (rc) return rc;
     }
     const int smem = q.nhb * q.halo_stride + q.S * q.wst_bytes + MISC;
-    static int attr_max = 0;
-    if (smem > attr_max) {
-        cudaError_t e = cudaFuncSetAttribute(hconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int attr_max[2] = {0, 0};
+    if (smem > attr_max[q.MT - 1]) {
+        cudaError_t e = q.MT == 2 ? cudaFuncSetAttribute(hconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                  : cudaFuncSetAttribute(hconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr_max = smem;
+        attr_max[q.MT - 1] = smem;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
-    if (cudaError_t le = vqb_launch(hconv_kernel, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)) return (int)le;
+    const cudaError_t le = q.MT == 2 ? vqb_launch(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)
+                                     : vqb_launch(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q);
+    if (le != cudaSuccess) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }

@@ -40,16 +40,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Wait for the phase with the given parity.  try_wait carries a suspend-time hint: the hardware parks the thread until
+// the phase completes (or the hint expires) instead of returning early and being re-polled.  Without the hint a waiting
+// warp re-executes try_wait + branch a few hundred times per microsecond: in the persistent kernels (8-12 warps parked on
+// barriers most of the time) those polls were ~20 % of all issued instructions and competed with the single MMA-issuer
+// warp for issue slots (profiles/r02_vq2_poll_loops.txt).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "LAB_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra LAB_DONE_%=;\n\t"
         "bra LAB_WAIT_%=;\n\t"
         "LAB_DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 
 // Waiting variant for warps that wait LONG (an epilogue waiting for a whole GEMM): back off with

@@ -29,7 +29,7 @@ int hconv_plan_rows(int kind, int Cin, int Cout);
 
 namespace {
 
-constexpr int RB_THREADS = 512;       // warps: 0 producer, 1 MMA issuer, 2 TMEM + weights, 4-11 epilogue 2, 12-15 epilogue 1
+constexpr int RB_THREADS = 512;       // warps: 0 halo producer, 1 MMA issuer, 2 TMEM + weights, 3 skip producer, 4-11 epilogue 2, 12-15 epilogue 1
 constexpr int RB_NHB = 3;             // halo buffers, rotating over the (tile, chunk) sequence
 
 struct ResBfParams {
@@ -112,16 +112,42 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
+            // the halo tiles two and three tiles ahead go to L2 now (3 halo buffers = 1.5 tiles of shared-memory prefetch do
+            // not cover an HBM round trip when every SM is streaming)
+            for (int ahead = 2; ahead <= 3; ++ahead) {
+                long long tp = tile + (long long)ahead * G;
+                if (leader && tp < ntiles) {
+                    const int px = (int)(tp % p.tiles_x); tp /= p.tiles_x;
+                    const int py = (int)(tp % p.tiles_y); tp /= p.tiles_y;
+                    for (int c = 0; c < chunks; ++c)
+                        asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::
+                                         "l"(reinterpret_cast<uint64_t>(&tma_in)), "r"(c * 64), "r"(px * 8 - 1), "r"((int)tp * p.BN), "r"(0),
+                                         "r"(py * p.BH - 1) : "memory");
+                }
+            }
             for (int c = 0; c < chunks; ++c) {
-                ptx::mbar_wait(hempty((int)hb), hpar ^ 1);
+                ptx::mbar_wait_sleep(hempty((int)hb), hpar ^ 1, 100);
                 if (leader) {
                     ptx::mbar_expect_tx(hfull((int)hb), (uint32_t)p.halo_bytes);
                     tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), c * 64, gx0 - 1, n0, 0, gy0 - 1);
                 }
                 if (++hb == RB_NHB) { hb = 0; hpar ^= 1; }
             }
+        }
+    } else if (warp == 3) {
+        // ===================== skip producer: the tile's own pixels into the staging buffers (epilogue 2 adds them) =====================
+        // A separate warp: behind the halo loads in one loop, the wait for the previous tile's store (sfree) kept the NEXT
+        // tile's halo request back until epilogue 2 had finished -- the halo then had less than one chunk time to arrive.
+        const bool leader = ptx::elect_one();
+        pdl_wait();
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+            long long t = tile;
+            const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
+            const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
+            const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
             for (int c = 0; c < chunks; ++c) {
-                ptx::mbar_wait(sfree(c), (uint32_t)((it & 1) ^ 1));           // the previous tile's store has read the buffer
+                ptx::mbar_wait_sleep(sfree(c), (uint32_t)((it & 1) ^ 1), 100);           // the previous tile's store has read the buffer
                 if (leader) {
                     ptx::mbar_expect_tx(sfull(c), 16384u);
                     tma_load_5d(sbase + st_off + (uint32_t)c * 16384u, &tma_skip, sfull(c), c * 64, gx0, n0, 0, gy0);
@@ -198,7 +224,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         unsigned char *arow = sm + a2_off + row * 128;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-            ptx::mbar_wait(d1full(it & 1), (uint32_t)((it >> 1) & 1));
+            ptx::mbar_wait_sleep(d1full(it & 1), (uint32_t)((it >> 1) & 1), 100);
             ptx::tc_fence_after();
             const uint32_t d1 = lane_t + (uint32_t)((it & 1) * Cmid);
             for (int c0 = 0; c0 < Cmid; c0 += 16) {
@@ -235,8 +261,8 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
             unsigned char *srow = sm + st_off + chunk * 16384 + row * 128;
-            ptx::mbar_wait(sfull(chunk), (uint32_t)(it & 1));
-            ptx::mbar_wait(d2full(it & 1), (uint32_t)((it >> 1) & 1));
+            ptx::mbar_wait_sleep(sfull(chunk), (uint32_t)(it & 1), 200);
+            ptx::mbar_wait_sleep(d2full(it & 1), (uint32_t)((it >> 1) & 1), 200);
             ptx::tc_fence_after();
             const uint32_t d2 = lane_t + D2COL + (uint32_t)((it & 1) * C);
             for (int c0 = col0; c0 < col0 + cpg; c0 += 32) {

@@ -35,7 +35,7 @@ constexpr int CN = 256;          // codes per chunk (UMMA N)
 constexpr int DD = 64;
 constexpr int NT2 = 512;         // 16 warps
 constexpr int NTRK = 16;         // trackers per thread
-constexpr int MAXC = 5;          // candidates a half row can hand over
+constexpr int MAXC = 3;          // candidates a half row can hand over (p99 of a whole row is 3); more -> whole-codebook scan
 constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
 constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
 constexpr int HIST_MAX = 1024;
@@ -43,11 +43,13 @@ constexpr int HIST_MAX = 1024;
 constexpr int OFF_Z = 0;
 constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;                    // float[2 * CN]
-constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x 8 ints
-constexpr int OFF_XCH = OFF_CAND + 2 * 256 * 32;             // float2[256]: (half-row min, partial ||z||^2)
-constexpr int OFF_Q = OFF_XCH + 256 * 8;                     // full-scan queue: int[132] (count + rows)
-constexpr int OFF_QR = OFF_Q + 132 * 4;                      // per finish warp (d, k) partials: 4 x (float,int) x 8 slots
-constexpr int OFF_HIST = OFF_QR + 4 * 8 * 8;
+constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x 4 ints (count, 3 codes)
+constexpr int OFF_XCH = OFF_CAND + 2 * 256 * 16;             // float2[256]: (half-row min, partial ||z||^2)
+constexpr int PCAP = 512;                                    // (row, code) pairs re-scored per tile (typically ~45)
+constexpr int OFF_Q = OFF_XCH + 256 * 8;                     // per tile parity: int[136] = full-scan queue (count + rows) + pair count
+constexpr int OFF_QR = OFF_Q + 2 * 136 * 4;                  // per finish warp (d, k) partials: 4 x (float,int) x 8 slots
+constexpr int OFF_PAIR = OFF_QR + 4 * 8 * 8;                 // pairs: int2 (row, k)[PCAP] then float dist[PCAP]
+constexpr int OFF_HIST = OFF_PAIR + PCAP * 12;
 constexpr int OFF_BAR = OFF_HIST + HIST_MAX * 4;
 constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
 constexpr int OFF_RED = OFF_TMEM + 64;
@@ -98,7 +100,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
     int *hist_s = reinterpret_cast<int *>(sm + OFF_HIST);
     int *cand = reinterpret_cast<int *>(sm + OFF_CAND);
     float2 *xch = reinterpret_cast<float2 *>(sm + OFF_XCH);
-    volatile int *fq = reinterpret_cast<volatile int *>(sm + OFF_Q);
+    volatile int *fq_all = reinterpret_cast<volatile int *>(sm + OFF_Q);
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
 
     const long long ntiles = (p.N + TM - 1) / TM;
@@ -123,7 +125,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
     }
     if (smem_hist)
         for (int k = tid; k < p.K; k += NT2) hist_s[k] = 0;
-    if (tid == 0) fq[0] = 0;
+    if (tid == 0) { fq_all[0] = 0; fq_all[135] = 0; fq_all[136] = 0; fq_all[136 + 135] = 0; }
     if (warp == 2) ptx::tmem_alloc(sbase + OFF_TMEM, 512);
     ptx::tc_fence_before();
     __syncthreads();
@@ -142,7 +144,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             long long tile = blockIdx.x;
             auto drain = [&](int jt, long long jtile) {      // z_q of tile jt is complete in its z stage: store it
                 const int zs = jt & 1;
-                ptx::mbar_wait(bar(Q_DONE + zs), (jt >> 1) & 1);
+                ptx::mbar_wait_sleep(bar(Q_DONE + zs), (jt >> 1) & 1, 100);
                 const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
                 tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
                 if (!p.zq_bf16) tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
@@ -254,7 +256,6 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             ptx::named_bar_sync(5, 256);
             Emax = mx;
             bad_codebook = bad != 0u;
-            if (et == 0) { fq[130] = __float_as_int(Emax); fq[131] = bad_codebook ? 1 : 0; }     // for the finish warps
         } else {
             Emax = __uint_as_float(reinterpret_cast<const unsigned *>(p.scal)[0]);
             bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
@@ -266,7 +267,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
             const unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
-            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 100);
             // this thread's half of ||z||^2 (any order: it only feeds the error bound tau)
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -284,7 +285,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 const long long gc = (long long)it * nchunks + c;
                 const int ab = (int)(gc & 1);
                 const int es = resident ? c : (int)(gc & 1);
-                ptx::mbar_wait(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1));
+                ptx::mbar_wait_sleep(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1), 64);
                 ptx::tc_fence_after();
                 const float *bch = bsm + es * CN + h * 128;
                 const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
@@ -373,8 +374,8 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 if (m2[i] <= thr) needfull = true;
             }
             const int par = it & 1;
-            ptx::mbar_wait(bar(C_EMPTY + par), (uint32_t)(((it >> 1) & 1) ^ 1));       // finish warps are done with tile it-2's records
-            int *rec = cand + (par * 256 + et) * 8;
+            ptx::mbar_wait_sleep(bar(C_EMPTY + par), (uint32_t)(((it >> 1) & 1) ^ 1), 100);       // finish warps are done with tile it-2's records
+            int *rec = cand + (par * 256 + et) * 4;
             rec[0] = needfull ? -1 : n;
 #pragma unroll
             for (int s = 0; s < MAXC; ++s) rec[1 + s] = ids[s];
@@ -387,150 +388,127 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
         const int row = ft, rsw = row & 7;
         double sse = 0.0;
         float *qr = reinterpret_cast<float *>(sm + OFF_QR);
+        int2 *prk = reinterpret_cast<int2 *>(sm + OFF_PAIR);
+        float *pdist = reinterpret_cast<float *>(sm + OFF_PAIR + PCAP * 8);
+        // canonical distance of code k to the z row at `zr_s` (shared memory, swizzled): A = sum fl(z^2) left to right,
+        // M = one sequential fmaf chain, d = fl(fl(A + B_k) - fl(2 M))   (quantizer.py:49-51, oracle.c)
+        auto exact_dist = [&](const unsigned char *zr_s, int zsw, int k) -> float {
+            float A = 0.f, M = 0.f;
+            const unsigned char *es = code_ptr_smem(k);
+            const float4 *eg = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);
+#pragma unroll
+            for (int c16 = 0; c16 < 16; ++c16) {
+                const float4 v = *reinterpret_cast<const float4 *>(zr_s + (c16 >> 3) * ZATOM + (((c16 & 7) ^ zsw) << 4));
+                const float4 e = resident ? *reinterpret_cast<const float4 *>(es + (c16 >> 3) * EATOM + (((c16 & 7) ^ (k & 7)) << 4)) : __ldg(eg + c16);
+                A = __fadd_rn(A, __fmul_rn(v.x, v.x)); A = __fadd_rn(A, __fmul_rn(v.y, v.y));
+                A = __fadd_rn(A, __fmul_rn(v.z, v.z)); A = __fadd_rn(A, __fmul_rn(v.w, v.w));
+                M = __fmaf_rn(v.x, e.x, M); M = __fmaf_rn(v.y, e.y, M); M = __fmaf_rn(v.z, e.z, M); M = __fmaf_rn(v.w, e.w, M);
+            }
+            const float bnk = resident ? bsm[k] : __ldg(p.bn + k);
+            return __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));
+        };
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1, par = it & 1;
-            unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
-            ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
-            ptx::mbar_wait(bar(C_FULL + par), (uint32_t)((it >> 1) & 1));
-            float Emax = 0.f;
-            (void)Emax;
-            // z row -> registers
-            float zr[DD];
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
-                    const float4 v = *reinterpret_cast<const float4 *>(zrow + a * ZATOM + ((c16 ^ rsw) << 4));
-                    zr[a * 32 + c16 * 4 + 0] = v.x; zr[a * 32 + c16 * 4 + 1] = v.y;
-                    zr[a * 32 + c16 * 4 + 2] = v.z; zr[a * 32 + c16 * 4 + 3] = v.w;
-                }
-            const int *r0 = cand + (par * 256 + row) * 8, *r1 = cand + (par * 256 + 128 + row) * 8;
+            volatile int *fq = fq_all + par * 136;                 // [0] queue count, [1..128] queued rows, [135] pair count
+            unsigned char *ztile = sm + OFF_Z + zs * ZSTAGE;
+            unsigned char *zrow = ztile + row * 128;
+            ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 200);
+            ptx::mbar_wait_sleep(bar(C_FULL + par), (uint32_t)((it >> 1) & 1), 200);
+            const int *r0 = cand + (par * 256 + row) * 4, *r1 = cand + (par * 256 + 128 + row) * 4;
             const int n0 = r0[0], n1 = r1[0];
-            int bk = -1;
+            int bk = -1, pbase = -1;
             float bd = 0.f;
-            // canonical A_i = sum_d fl(z^2), left to right (quantizer.py:49) -- needed by every exact distance
-            float A = 0.f;
-#pragma unroll
-            for (int d = 0; d < DD; ++d) A = __fadd_rn(A, __fmul_rn(zr[d], zr[d]));
-            auto exact_code = [&](int k) {       // canonical distance of code k; keeps the better of (bd,bk) and it
-                float M = 0.f;
-                float bnk;
-                if (resident) {
-                    const unsigned char *er = code_ptr_smem(k);
-#pragma unroll
-                    for (int a = 0; a < 2; ++a)
-#pragma unroll
-                        for (int c16 = 0; c16 < 8; ++c16) {
-                            const float4 e = *reinterpret_cast<const float4 *>(er + a * EATOM + ((c16 ^ (k & 7)) << 4));
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 0], e.x, M); M = __fmaf_rn(zr[a * 32 + c16 * 4 + 1], e.y, M);
-                            M = __fmaf_rn(zr[a * 32 + c16 * 4 + 2], e.z, M); M = __fmaf_rn(zr[a * 32 + c16 * 4 + 3], e.w, M);
-                        }
-                    bnk = bsm[k];
-                } else {
-                    const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);
-#pragma unroll
-                    for (int c16 = 0; c16 < 16; ++c16) {
-                        const float4 e = __ldg(er + c16);
-                        M = __fmaf_rn(zr[c16 * 4 + 0], e.x, M); M = __fmaf_rn(zr[c16 * 4 + 1], e.y, M);
-                        M = __fmaf_rn(zr[c16 * 4 + 2], e.z, M); M = __fmaf_rn(zr[c16 * 4 + 3], e.w, M);
-                    }
-                    bnk = __ldg(p.bn + k);
+            const int ncand = n0 + n1;
+            bool queued = n0 < 0 || n1 < 0;
+            if (!queued && ncand == 1) {
+                bk = n0 == 1 ? r0[1] : r1[1];            // the only code inside the window: provably the canonical argmin
+            } else if (!queued) {
+                // 2..10 candidates: their (row, code) pairs join the tile's work list, re-scored densely below
+                pbase = atomicAdd(const_cast<int *>(&fq[135]), ncand);
+                if (pbase + ncand > PCAP) { queued = true; pbase = -1; }
+                else {
+                    for (int s2 = 0; s2 < n0; ++s2) prk[pbase + s2] = make_int2(row, r0[1 + s2]);
+                    for (int s2 = 0; s2 < n1; ++s2) prk[pbase + n0 + s2] = make_int2(row, r1[1 + s2]);
                 }
-                const float dist = __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));   // quantizer.py:49-51
-                if (bk < 0 || vq2_better(dist, k, bd, bk)) { bd = dist; bk = k; }
-            };
-            const bool queued = n0 < 0 || n1 < 0;
+            }
             if (queued) {
                 const int slot = atomicAdd(const_cast<int *>(&fq[0]), 1);
                 fq[1 + slot] = row;
-            } else if (n0 + n1 == 1) {
-                bk = n0 == 1 ? r0[1] : r1[1];            // the only code inside the window: provably the canonical argmin
-            } else {
-                for (int s = 0; s < n0; ++s) { const int k = r0[1 + s]; if (k < p.K) exact_code(k); }
-                for (int s = 0; s < n1; ++s) { const int k = r1[1 + s]; if (k < p.K) exact_code(k); }
             }
-            ptx::named_bar_sync(6, 128);                   // the queue is complete
-            const int nq = fq[0];
-            if (nq > 0) {
-                // whole-codebook exact scans, all 128 finish threads per queued row: thread t takes codes t, t+128, ...
-                for (int qi = 0; qi < nq; ++qi) {
-                    const int qrow = fq[1 + qi];
-                    const unsigned char *qz = sm + OFF_Z + zs * ZSTAGE + qrow * 128;
-                    float qA = 0.f;
-                    // canonical norm of the queued row (broadcast loads)
-#pragma unroll
-                    for (int a = 0; a < 2; ++a)
-#pragma unroll
-                        for (int c16 = 0; c16 < 8; ++c16) {
-                            const float4 v = *reinterpret_cast<const float4 *>(qz + a * ZATOM + ((c16 ^ (qrow & 7)) << 4));
-                            qA = __fadd_rn(qA, __fmul_rn(v.x, v.x)); qA = __fadd_rn(qA, __fmul_rn(v.y, v.y));
-                            qA = __fadd_rn(qA, __fmul_rn(v.z, v.z)); qA = __fadd_rn(qA, __fmul_rn(v.w, v.w));
-                        }
-                    float sd = 0.f;
-                    int sk = -1;
-                    for (int k = ft; k < p.K; k += 128) {
-                        float M = 0.f;
-                        const float4 *er = reinterpret_cast<const float4 *>(p.E + (size_t)k * DD);     // streamed codebooks: through L2
-                        const unsigned char *es = code_ptr_smem(k);                                     // resident: shared memory
-#pragma unroll
-                        for (int c16 = 0; c16 < 16; ++c16) {
-                            const float4 e = resident ? *reinterpret_cast<const float4 *>(es + (c16 >> 3) * EATOM + (((c16 & 7) ^ (k & 7)) << 4))
-                                                      : __ldg(er + c16);
-                            const float4 v = *reinterpret_cast<const float4 *>(qz + (c16 >> 3) * ZATOM + (((c16 & 7) ^ (qrow & 7)) << 4));
-                            M = __fmaf_rn(v.x, e.x, M); M = __fmaf_rn(v.y, e.y, M); M = __fmaf_rn(v.z, e.z, M); M = __fmaf_rn(v.w, e.w, M);
-                        }
-                        const float bnk = resident ? bsm[k] : __ldg(p.bn + k);
-                        const float dist = __fsub_rn(__fadd_rn(qA, bnk), __fmul_rn(2.0f, M));
-                        if (sk < 0 || vq2_better(dist, k, sd, sk)) { sd = dist; sk = k; }
-                    }
-                    // warp reduce, then 4 warp partials through shared memory
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const float od = __shfl_xor_sync(0xffffffffu, sd, off);
-                        const int ok = __shfl_xor_sync(0xffffffffu, sk, off);
-                        if (ok >= 0 && (sk < 0 || vq2_better(od, ok, sd, sk))) { sd = od; sk = ok; }
-                    }
-                    if (lane == 0) { qr[((warp - 12) * 8 + (qi & 7)) * 2] = sd; reinterpret_cast<int *>(qr)[((warp - 12) * 8 + (qi & 7)) * 2 + 1] = sk; }
-                    ptx::named_bar_sync(6, 128);
-                    if (row == qrow) {
-                        for (int w = 0; w < 4; ++w) {
-                            const float od = qr[(w * 8 + (qi & 7)) * 2];
-                            const int ok = reinterpret_cast<int *>(qr)[(w * 8 + (qi & 7)) * 2 + 1];
-                            if (ok >= 0 && (bk < 0 || vq2_better(od, ok, bd, bk))) { bd = od; bk = ok; }
-                        }
-                    }
-                    if ((qi & 7) == 7) ptx::named_bar_sync(6, 128);      // the 8 partial slots are recycled
+            ptx::named_bar_sync(6, 128);                   // work list and queue are complete
+            {
+                const int np = min((int)fq[135], PCAP);
+                for (int pi = ft; pi < np; pi += 128) {
+                    const int2 rk = prk[pi];
+                    pdist[pi] = exact_dist(ztile + rk.x * 128, rk.x & 7, rk.y);
                 }
-                ptx::named_bar_sync(6, 128);
-                if (ft == 0) fq[0] = 0;
-                ptx::named_bar_sync(6, 128);               // (the reset is visible before any push of the next tile)
             }
+            const int nq = fq[0];
+            // whole-codebook exact scans, all 128 finish threads per queued row: thread t takes codes t, t+128, ...
+            for (int qi = 0; qi < nq; ++qi) {
+                const int qrow = fq[1 + qi];
+                float sd = 0.f;
+                int sk = -1;
+                for (int k = ft; k < p.K; k += 128) {
+                    const float dist = exact_dist(ztile + qrow * 128, qrow & 7, k);
+                    if (sk < 0 || vq2_better(dist, k, sd, sk)) { sd = dist; sk = k; }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, sd, off);
+                    const int ok = __shfl_xor_sync(0xffffffffu, sk, off);
+                    if (ok >= 0 && (sk < 0 || vq2_better(od, ok, sd, sk))) { sd = od; sk = ok; }
+                }
+                if (lane == 0) { qr[((warp - 12) * 8 + (qi & 7)) * 2] = sd; reinterpret_cast<int *>(qr)[((warp - 12) * 8 + (qi & 7)) * 2 + 1] = sk; }
+                ptx::named_bar_sync(6, 128);
+                if (row == qrow) {
+                    for (int w = 0; w < 4; ++w) {
+                        const float od = qr[(w * 8 + (qi & 7)) * 2];
+                        const int ok = reinterpret_cast<int *>(qr)[(w * 8 + (qi & 7)) * 2 + 1];
+                        if (ok >= 0 && (bk < 0 || vq2_better(od, ok, bd, bk))) { bd = od; bk = ok; }
+                    }
+                }
+                if ((qi & 7) == 7) ptx::named_bar_sync(6, 128);      // the 8 partial slots are recycled
+            }
+            ptx::named_bar_sync(6, 128);                   // pair distances (and queue results) are complete
+            if (pbase >= 0) {
+                for (int s2 = 0; s2 < ncand; ++s2) {
+                    const int k = prk[pbase + s2].y;
+                    const float dist = pdist[pbase + s2];
+                    if (k < p.K && (bk < 0 || vq2_better(dist, k, bd, bk))) { bd = dist; bk = k; }
+                }
+            }
+            if (ft == 0) { fq[0] = 0; fq[135] = 0; }      // this parity's counters are next used two tiles (>= two barriers) later
             if (bk < 0) bk = 0;
 
             // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram, idx ----
             const long long grow = tile * TM + row;
             const bool live = grow < p.N;
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;     // this row's sum of (e - z)^2: 4 fp32 partials, one double add per row
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float o[8];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c16 = 2 * c8 + u;                  // 16-byte piece of the 256-byte fp32 row
+                    const float4 zv = *reinterpret_cast<const float4 *>(zrow + (c16 >> 3) * ZATOM + (((c16 & 7) ^ rsw) << 4));
                     float4 e4;
                     if (resident) e4 = *reinterpret_cast<const float4 *>(code_ptr_smem(bk) + (c16 >> 3) * EATOM + (((c16 & 7) ^ (bk & 7)) << 4));
                     else e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)bk * DD) + c16);
                     float4 df;
-                    df.x = __fsub_rn(e4.x, zr[c16 * 4 + 0]); df.y = __fsub_rn(e4.y, zr[c16 * 4 + 1]);
-                    df.z = __fsub_rn(e4.z, zr[c16 * 4 + 2]); df.w = __fsub_rn(e4.w, zr[c16 * 4 + 3]);
-                    o[4 * u + 0] = __fadd_rn(zr[c16 * 4 + 0], df.x); o[4 * u + 1] = __fadd_rn(zr[c16 * 4 + 1], df.y);     // quantizer.py:67
-                    o[4 * u + 2] = __fadd_rn(zr[c16 * 4 + 2], df.z); o[4 * u + 3] = __fadd_rn(zr[c16 * 4 + 3], df.w);
-                    if (live) sse += (double)df.x * df.x + (double)df.y * df.y + (double)df.z * df.z + (double)df.w * df.w;
+                    df.x = __fsub_rn(e4.x, zv.x); df.y = __fsub_rn(e4.y, zv.y); df.z = __fsub_rn(e4.z, zv.z); df.w = __fsub_rn(e4.w, zv.w);
+                    o[4 * u + 0] = __fadd_rn(zv.x, df.x); o[4 * u + 1] = __fadd_rn(zv.y, df.y);     // quantizer.py:67
+                    o[4 * u + 2] = __fadd_rn(zv.z, df.z); o[4 * u + 3] = __fadd_rn(zv.w, df.w);
+                    rs0 = fmaf(df.x, df.x, rs0); rs1 = fmaf(df.y, df.y, rs1); rs2 = fmaf(df.z, df.z, rs2); rs3 = fmaf(df.w, df.w, rs3);
                     if (!p.zq_bf16)
                         *reinterpret_cast<float4 *>(zrow + (c16 >> 3) * ZATOM + (((c16 & 7) ^ rsw) << 4)) =
                             make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
                 }
                 if (p.zq_bf16) {
+                    // bf16 rows (128 B) over the first atom: piece c8 holds channels 8 c8 .. 8 c8 + 7.  It overwrites fp32 piece
+                    // c8 of atom 0 (channels 4 c8 ..), which this thread has already consumed (pieces are read in order 2 c8, 2 c8 + 1
+                    // >= c8) -- except nothing: piece index c8 <= 2 c8 always.
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
                     *reinterpret_cast<uint4 *>(zrow + ((c8 ^ rsw) << 4)) =
@@ -539,6 +517,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 }
             }
             if (live) {
+                sse += (double)((rs0 + rs1) + (rs2 + rs3));
                 p.idx[grow] = bk;
                 if (smem_hist) atomicAdd(&hist_s[bk], 1);
                 else atomicAdd(&p.hist[bk], 1);
