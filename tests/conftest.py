@@ -25,3 +25,12 @@ def _fp32_unless_stated():
     vqvae_b200.set_precision("fp32")
     yield
     vqvae_b200.set_precision("fp32")
+
+
+@pytest.fixture(autouse=True)
+def _inference_unless_stated():
+    """The forward path is the product: tests run under ``torch.no_grad()`` like the notebook's
+    ``reconstruct``; the two tests of the differentiable VectorQuantizer re-enable grad themselves."""
+    import torch
+    with torch.no_grad():
+        yield

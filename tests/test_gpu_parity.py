@@ -56,11 +56,13 @@ def test_vq_module_five_tuple_matches_reference():
     vq = VectorQuantizer(512, 64, 0.25)
     vq.embedding.weight.data.copy_(torch.from_numpy(E))
     vq = vq.cuda()
-    loss, z_q, perp, onehot, idx = vq(_cuda(z))
+    with torch.enable_grad():                  # grad mode + a trainable codebook: the differentiable path, like the reference
+        loss, z_q, perp, onehot, idx = vq(_cuda(z))
     assert idx.shape == (z.shape[0] * z.shape[2] * z.shape[3], 1) and idx.dtype == torch.int64
     assert np.array_equal(idx.cpu().numpy(), g["idx"])
     assert z_q.shape == z.shape and z_q.is_contiguous()
-    assert np.array_equal(z_q.cpu().numpy(), g["z_q"])
+    assert z_q.requires_grad
+    assert np.array_equal(z_q.detach().cpu().numpy(), g["z_q"])
     assert onehot.shape == (idx.shape[0], 512) and onehot.dtype == torch.float32
     oh = onehot.cpu().numpy()
     assert np.array_equal(oh.argmax(1), g["idx"].ravel()) and np.all(oh.sum(1) == 1.0)
@@ -169,6 +171,39 @@ TC_CONV_CASES = [
     (2, 3, 32, 32, 128, 4, 2, 1, False, 0, 1, True, False),    # fast path, Cout=128 (direct stores)
     (3, 3, 6, 8, 64, 4, 2, 1, False, 0, 1, True, False),       # partial tile (36 pixels), TMA store clips
 ]
+
+
+def test_tf32_full_size_properties_cfg2():
+    """BASELINE cfg2 at its full size (B=256, 32x32, K=512) in the default VQB_TF32 mode, through size-independent
+    properties: (1) the VQ step is bit-exact on the z_e the TF32 encoder produced (C oracle on all 16384 rows);
+    (2) z_e is within 1e-3 of the all-fp32 product forward (itself oracle-checked at small sizes); (3) the share of
+    min_encoding_indices that differ from the all-fp32 forward stays below 0.5 %; (4) the decoder output is within
+    1.5e-3 of the fp32 decoder run on the SAME codes."""
+    import vqvae_b200
+    from vqvae_b200.synth import make_images, make_state_dict
+    hp = dict(h_dim=128, res_h_dim=32, n_res_layers=2, n_embeddings=512, embedding_dim=64)
+    sd = make_state_dict(seed=0, codebook="normal", codebook_scale=0.05, **hp)
+    m = build_model(hp, sd)
+    x = _cuda(make_images(256, 32, seed=1))
+    with vqvae_b200.precision("fp32"):
+        ze32, B, H, W = m._encode_rows(x.clone())
+        m(x.clone())
+        idx32 = m.last_min_encoding_indices.clone()
+    with vqvae_b200.precision("tf32"):
+        ze, B, H, W = m._encode_rows(x.clone())
+        loss, x_hat, perp = m(x.clone())
+        idx = m.last_min_encoding_indices.clone()
+    assert (ze - ze32).abs().max().item() <= 1e-3
+    rows = ze.reshape(-1, 64).cpu().numpy()
+    o = cref.vq_rows(rows, sd["vector_quantization.embedding.weight"])
+    assert np.array_equal(idx.cpu().numpy().ravel(), o["idx"])
+    np.testing.assert_allclose(loss.item(), 1.25 * o["sse"] / rows.size, rtol=1e-5)
+    flips = float((idx != idx32).float().mean().item())
+    assert flips <= 0.005, flips
+    with vqvae_b200.precision("fp32"):
+        xh32 = m.decoder(_cuda(np.ascontiguousarray(o["zq"].reshape(B, H, W, 64).transpose(0, 3, 1, 2))))
+    assert (x_hat - xh32).abs().max().item() <= 1.5e-3
+    print("cfg2 full size tf32: flips vs fp32 %.4f %%" % (100 * flips))
 
 
 @pytest.mark.parametrize("case", TC_CONV_CASES)
@@ -397,6 +432,7 @@ def test_vq_backward_matches_autograd_of_the_reference_formula():
     z0 = rng.standard_normal((3, D, 5, 7)).astype(np.float32)
     E0 = rng.standard_normal((K, D)).astype(np.float32)
     gq = rng.standard_normal((3, D, 5, 7)).astype(np.float32)
+    torch.set_grad_enabled(True)               # (the conftest default is no_grad; restored by its context on exit)
     # reference formula with torch autograd (CPU)
     z = torch.tensor(z0, requires_grad=True)
     E = torch.tensor(E0, requires_grad=True)

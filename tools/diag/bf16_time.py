@@ -49,3 +49,10 @@ p1, p2 = ops.pack_conv_weight_bf16(w1, _lib.CONV_K3), ops.pack_conv_weight_bf16(
 us = t(lambda: ops.residual_layer_bf16(r, p1, p2, B=B, H=L, W=L, C=128, Cmid=32, relu_out=True))
 fl = 2 * B * L * L * (9 * 128 * 32 + 32 * 128)
 print(f"{'res 128->32->128':28s} {us:9.1f} us   {fl / us / 1e6:8.1f} TFLOP/s   {2 * B * L * L * 128 * 2 / us / 1e3:7.1f} GB/s", flush=True)
+
+x = torch.rand((B, 3, S, S), device=dev, generator=g) * 2 - 1
+wi = torch.randn((64, 3, 4, 4), device=dev, generator=g) / 7
+pi = ops.pack_conv_weight(wi, False)
+bi = torch.zeros((64,), device=dev)
+us = t(lambda: ops.conv_in_bf16(x, pi, bi, B=B, H=S, W=S, Cout=64))
+print(f"{'E1 conv 3->64 k4s2 (f32 in)':28s} {us:9.1f} us   {(B * 3 * S * S * 4 + B * S * S // 4 * 64 * 2) / us / 1e3:7.1f} GB/s", flush=True)

@@ -49,7 +49,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (sbase - raw);
     // [A x2][B: 2 atoms][staging 16 KB][raw rows x2][barriers, bias]
-    const uint32_t b_off = 2 * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + 16384u;
+    const uint32_t b_off = 2 * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + 2 * 16384u;      // (two staging tiles)
     const uint32_t raw_stride = ((uint32_t)p.raw_bytes + 127u) & ~127u;
     const uint32_t bar_off = raw_off + NRAW * raw_stride;
     const uint32_t bars = sbase + bar_off;
@@ -59,7 +59,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     auto aempty = [&](int s) { return bars + 8u * (2 * NRAW + 2 + s); };
     auto tfull = [&](int s) { return bars + 8u * (2 * NRAW + 4 + s); };
     auto tempty = [&](int s) { return bars + 8u * (2 * NRAW + 6 + s); };
-    const uint32_t sfree = bars + 8u * (2 * NRAW + 8);
+    auto sfree = [&](int s) { return bars + 8u * (2 * NRAW + 8 + s); };
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 10));
     float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 12));
 
@@ -71,7 +71,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             ptx::mbar_init(afull(s), 8); ptx::mbar_init(aempty(s), 1);
             ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4);
         }
-        ptx::mbar_init(sfree, 1);
+        ptx::mbar_init(sfree(0), 1); ptx::mbar_init(sfree(1), 1);
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tma_x); ptx::prefetch_tmap(&tma_out);
     }
@@ -136,8 +136,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         uint32_t rs = 0, rpar = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             const int s = it & 1;
-            ptx::mbar_wait_sleep(rfull((int)rs), rpar, 100);
-            ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1), 100);
+            ptx::mbar_wait_sleep(rfull((int)rs), rpar, 32);
+            ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1), 32);
             const float *rawp = reinterpret_cast<const float *>(sm + raw_off + rs * raw_stride);
             float v[24];                                          // k_local = (trl*4 + s)*3 + c
 #pragma unroll
@@ -168,12 +168,11 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         // ===================== epilogue: thread = pixel row; bias, ReLU, bf16, staged tile, one TMA store =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        unsigned char *orow = sm + st_off + row * 128;
         const bool storer = tid == 384;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             const int s = it & 1;
-            ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it >> 1) & 1), 100);
+            ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it >> 1) & 1), 32);
             ptx::tc_fence_after();
             float va[32], vb[32];
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * COUT);
@@ -184,7 +183,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty(s));          // the accumulator is in registers
-            ptx::mbar_wait(sfree, (uint32_t)((it & 1) ^ 1));       // the previous tile's TMA store has read the staging buffer
+            unsigned char *orow = sm + st_off + s * 16384 + row * 128;
+            ptx::mbar_wait(sfree(s), (uint32_t)(((it >> 1) & 1) ^ 1));       // the store of tile it-2 has read this staging buffer
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -205,10 +205,10 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             ptx::named_bar_sync(1, 128);
             if (storer) {
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
-                                 "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + st_off), "r"(0), "r"((int)(tile * 128)) : "memory");
+                                 "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + st_off + (uint32_t)s * 16384u), "r"(0), "r"((int)(tile * 128)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                ptx::mbar_arrive(sfree);
+                ptx::mbar_arrive(sfree(s));
             }
         }
         if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -251,7 +251,7 @@ int launch_conv_in_bf16_persistent(const float *x, const float *wp, const float 
         if (rc) return rc;
     }
     const int raw_stride = (q.raw_bytes + 127) & ~127;
-    const int smem = 2 * (int)A_BYTES + 2 * (int)B_ATOM + 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 12) + COUT * 4 + 1024;
+    const int smem = 2 * (int)A_BYTES + 2 * (int)B_ATOM + 2 * 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 12) + COUT * 4 + 1024;
     if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
     static int attr_max = 0;
     if (smem > attr_max) {

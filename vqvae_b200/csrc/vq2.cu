@@ -8,14 +8,18 @@
 //
 // What changed (profiles/r01_vq_tc_epilogue_timeline.txt: 8.7 us per 128-row tile against a 1.5 us HBM budget, all
 // phases serial, every row re-scoring 8-16 codes although 82-86 % of the rows have ONE code inside the window):
-//   * the sweep over the scores works at ELEMENT level: the code's position is packed into the low mantissa bits of
-//     its score (one LOP3; the perturbation, 2^-(23-nbits) relative, is added to tau) and every thread keeps 16
-//     (min, second-min) trackers, one per column residue mod 16 -- 4.75 instructions per score, no lists, no branches;
-//   * after the sweep a row's window is known exactly whenever no tracker holds TWO codes inside it (then a third
-//     might hide behind them): candidates = {tracker minima <= min + tau}.  One candidate -> it is the canonical
-//     argmin, NO exact arithmetic at all (the common case); 2..10 candidates -> those codes only are re-scored;
-//     two in one tracker (1/32 of the multi-candidate rows), non-finite data or overflow -> the row is queued and all
-//     finish threads scan the whole codebook for it together;
+//   * the sweep over the scores only takes MINIMA, over several partitions of a thread's codes at once: P1 = the
+//     column's residue mod 16 (16 running minima), P2 = its 16-column block inside the chunk pair (16 minima, reduced
+//     by a min3 tree as the block passes), and for streamed codebooks P3 / P4 = the chunk pair mod 8 / div 8.  That is
+//     one 3-input FMNMX per score (plus the FFMA that forms the score) -- no index packing, no second minima, no
+//     lists, no branches (profiles/r02_vq2_profile_notes.txt: the first version's 4.5 ALU-pipe instructions per score
+//     were the kernel's bound);
+//   * after the sweep the window {s_k <= min + tau} is covered exactly by a GRID: a code inside the window pulls the
+//     minimum of every class it belongs to under the threshold, so window is a subset of R x B x C x Q with R, B, C, Q
+//     the classes whose minimum is inside the window.  One grid point -> it is the canonical argmin, NO exact
+//     arithmetic at all (82-86 % of the rows); a few -> those codes are re-scored with the canonical chain (grid points
+//     outside the window are harmless: the exact distance decides); a big grid, non-finite data or overflow -> the row
+//     is queued and all finish threads scan the whole codebook for it together;
 //   * sweep (8 warps, TMEM readers) and finish (4 warps: decision, exact chains, gather, z_q = z + (e - z), SSE,
 //     histogram, idx) are different warps and work on different tiles at the same time; the TMA producer / MMA issuer
 //     run ahead of both.  16 warps per CTA, one CTA per SM, persistent.
@@ -34,8 +38,8 @@ constexpr int TM = 128;          // latent rows per tile (UMMA M)
 constexpr int CN = 256;          // codes per chunk (UMMA N)
 constexpr int DD = 64;
 constexpr int NT2 = 512;         // 16 warps
-constexpr int NTRK = 16;         // trackers per thread
-constexpr int MAXC = 3;          // candidates a half row can hand over (p99 of a whole row is 3); more -> whole-codebook scan
+constexpr int NTRK = 16;         // minima per partition and thread
+constexpr int GCAP = 24;         // grid points a half row can hand over; more -> whole-codebook scan
 constexpr int ZSTAGE = TM * DD * 4, ZATOM = TM * 128;
 constexpr int ESTAGE = CN * DD * 4, EATOM = CN * 128;
 constexpr int HIST_MAX = 1024;
@@ -43,9 +47,9 @@ constexpr int HIST_MAX = 1024;
 constexpr int OFF_Z = 0;
 constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;                    // float[2 * CN]
-constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x 4 ints (count, 3 codes)
+constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x int4 (grid size or -1, R | B << 16, C | Q << 8, 0)
 constexpr int OFF_XCH = OFF_CAND + 2 * 256 * 16;             // float2[256]: (half-row min, partial ||z||^2)
-constexpr int PCAP = 512;                                    // (row, code) pairs re-scored per tile (typically ~45)
+constexpr int PCAP = 1024;                                   // (row, code) pairs re-scored per tile (typically ~100)
 constexpr int OFF_Q = OFF_XCH + 256 * 8;                     // per tile parity: int[136] = full-scan queue (count + rows) + pair count
 constexpr int OFF_QR = OFF_Q + 2 * 136 * 4;                  // per finish warp (d, k) partials: 4 x (float,int) x 8 slots
 constexpr int OFF_PAIR = OFF_QR + 4 * 8 * 8;                 // pairs: int2 (row, k)[PCAP] then float dist[PCAP]
@@ -85,6 +89,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+template <bool RESIDENT>
 __global__ void __launch_bounds__(NT2, 1)
 vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme,
            const __grid_constant__ CUtensorMap tmq, const Vq2Params p) {
@@ -105,7 +110,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
 
     const long long ntiles = (p.N + TM - 1) / TM;
     const int nchunks = p.nchunks;
-    const bool resident = nchunks <= 2;
+    constexpr bool resident = RESIDENT;           // the whole codebook (<= 2 chunks) stays in shared memory
     const bool smem_hist = p.K <= HIST_MAX;
     const float INF = __int_as_float(0x7f800000);
 
@@ -261,7 +266,6 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             bad_codebook = reinterpret_cast<const unsigned *>(p.scal)[1] != 0u;
         }
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t keep = ~((1u << p.nbits) - 1u);
 
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -277,108 +281,126 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             }
             const float Apart = (a0 + a1) + (a2 + a3);
 
-            float m1[NTRK], m2[NTRK];
+            // running minima of the partitions (header): m1 residue mod 16, mb block of the chunk pair, mc / m4 chunk pair
+            float m1[NTRK], mb[NTRK], mc[8], m4[2];
 #pragma unroll
-            for (int i = 0; i < NTRK; ++i) { m1[i] = INF; m2[i] = INF; }
+            for (int i = 0; i < NTRK; ++i) { m1[i] = INF; mb[i] = INF; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mc[i] = INF;
+            m4[0] = INF; m4[1] = INF;
+            float cur = INF;                                          // minimum of the current chunk pair (streamed codebooks)
 
-            for (int c = 0; c < nchunks; ++c) {
-                const long long gc = (long long)it * nchunks + c;
-                const int ab = (int)(gc & 1);
-                const int es = resident ? c : (int)(gc & 1);
-                ptx::mbar_wait_sleep(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1), 64);
-                ptx::tc_fence_after();
-                const float *bch = bsm + es * CN + h * 128;
-                const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
-                const uint32_t cbase = (uint32_t)(c * 128);
-                float va[32], vb[32];
-                auto process = [&](const float (&v)[32], int j) {
-                    const uint32_t jb = cbase + (uint32_t)(j * 32);
-                    float bq[32];                                     // ||e_k||^2 of the 32 columns (broadcast 16-byte loads)
+            for (int c0 = 0; c0 < nchunks; c0 += 2) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(bch + j * 32 + 4 * i);
-                        bq[4 * i] = b4.x; bq[4 * i + 1] = b4.y; bq[4 * i + 2] = b4.z; bq[4 * i + 3] = b4.w;
-                    }
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = c0 + cc;
+                    if (c < nchunks) {
+                        const long long gc = (long long)it * nchunks + c;
+                        const int ab = (int)(gc & 1);
+                        const int es = resident ? c : (int)(gc & 1);
+                        ptx::mbar_wait_sleep(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1), 64);
+                        ptx::tc_fence_after();
+                        const float *bch = bsm + es * CN + h * 128;
+                        const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
+                        float va[32], vb[32];
+                        auto process = [&](const float (&v)[32], const int j) {
+                            float sc[32];
 #pragma unroll
-                    for (int i = 0; i < NTRK; ++i) {
-                        // scores of columns i and i+16 of this load, position packed into the low mantissa bits
-                        const float sa = fmaf(v[i], -2.f, bq[i]);
-                        const float sb = fmaf(v[i + 16], -2.f, bq[i + 16]);
-                        const float pa = __uint_as_float((__float_as_uint(sa) & keep) | (jb + (uint32_t)i));
-                        const float pb = __uint_as_float((__float_as_uint(sb) & keep) | (jb + (uint32_t)(i + 16)));
-                        const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
-                        const float t = fmaxf(m1[i], lo);
-                        m1[i] = fminf(m1[i], lo);
-                        m2[i] = ptx::fmin3(t, m2[i], hi);
+                            for (int i = 0; i < 8; ++i) {                 // ||e_k||^2 of the 32 columns (broadcast 16-byte loads)
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bch + j * 32 + 4 * i);
+                                sc[4 * i] = fmaf(v[4 * i], -2.f, b4.x); sc[4 * i + 1] = fmaf(v[4 * i + 1], -2.f, b4.y);
+                                sc[4 * i + 2] = fmaf(v[4 * i + 2], -2.f, b4.z); sc[4 * i + 3] = fmaf(v[4 * i + 3], -2.f, b4.w);
+                            }
+#pragma unroll
+                            for (int i = 0; i < NTRK; ++i) m1[i] = ptx::fmin3(m1[i], sc[i], sc[i + 16]);
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {                 // the two 16-column blocks of this load
+                                const float *b = sc + 16 * u;
+                                float &acc = mb[cc * 8 + j * 2 + u];
+                                const float t1 = ptx::fmin3(b[2], b[3], b[4]), t2 = ptx::fmin3(b[5], b[6], b[7]);
+                                const float t3 = ptx::fmin3(b[8], b[9], b[10]), t4 = ptx::fmin3(b[11], b[12], b[13]);
+                                const float t6 = ptx::fmin3(t1, t2, t3);
+                                if (resident) {
+                                    const float t0 = ptx::fmin3(acc, b[0], b[1]);
+                                    const float t5 = ptx::fmin3(b[14], b[15], t0);
+                                    acc = ptx::fmin3(t4, t5, t6);
+                                } else {
+                                    const float t0 = ptx::fmin3(b[0], b[1], b[14]);
+                                    const float t5 = ptx::fmin3(b[15], t0, t4);
+                                    const float blk = fminf(t5, t6);
+                                    acc = fminf(acc, blk);
+                                    cur = fminf(cur, blk);
+                                }
+                            }
+                        };
+                        ptx::tmem_ld32(tcol, va);
+                        ptx::tmem_ld_wait32(va);
+                        ptx::tmem_ld32(tcol + 32, vb);
+                        process(va, 0);
+                        ptx::tmem_ld_wait32(vb);
+                        ptx::tmem_ld32(tcol + 64, va);
+                        process(vb, 1);
+                        ptx::tmem_ld_wait32(va);
+                        ptx::tmem_ld32(tcol + 96, vb);
+                        process(va, 2);
+                        ptx::tmem_ld_wait32(vb);
+                        process(vb, 3);
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::mbar_arrive(bar(T_EMPTY + ab));
+                            if (!resident) ptx::mbar_arrive(bar(E_EMPTY + es));
+                        }
                     }
-                };
-                ptx::tmem_ld32(tcol, va);
-                ptx::tmem_ld_wait32(va);
-                ptx::tmem_ld32(tcol + 32, vb);
-                process(va, 0);
-                ptx::tmem_ld_wait32(vb);
-                ptx::tmem_ld32(tcol + 64, va);
-                process(vb, 1);
-                ptx::tmem_ld_wait32(va);
-                ptx::tmem_ld32(tcol + 96, vb);
-                process(va, 2);
-                ptx::tmem_ld_wait32(vb);
-                process(vb, 3);
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    ptx::mbar_arrive(bar(T_EMPTY + ab));
-                    if (!resident) ptx::mbar_arrive(bar(E_EMPTY + es));
+                }
+                if (!resident) {                                       // close the chunk pair
+                    const int cp = c0 >> 1;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (i == (cp & 7)) mc[i] = fminf(mc[i], cur);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) if (i == (cp >> 3)) m4[i] = fminf(m4[i], cur);
+                    cur = INF;
                 }
             }
 
             // ---- half-row minimum, exchange with the partner thread (same row, other column half) ----
-            float hmin = m1[0];
-#pragma unroll
-            for (int i = 1; i < NTRK; ++i) hmin = fminf(hmin, m1[i]);
+            float hmin;
+            {
+                const float t0 = ptx::fmin3(m1[0], m1[1], m1[2]), t1 = ptx::fmin3(m1[3], m1[4], m1[5]), t2 = ptx::fmin3(m1[6], m1[7], m1[8]);
+                const float t3 = ptx::fmin3(m1[9], m1[10], m1[11]), t4 = ptx::fmin3(m1[12], m1[13], m1[14]);
+                hmin = fminf(ptx::fmin3(t0, t1, t2), ptx::fmin3(t3, t4, m1[15]));
+            }
             xch[et] = make_float2(hmin, Apart);
             ptx::named_bar_sync(1 + q, 64);
             const float2 px = xch[et ^ 128];
             const float rowmin = fminf(hmin, px.x);
             const float A = Apart + px.y;
             // S >= sum_d |z_d e_kd| for every k (Cauchy-Schwarz, rounded up); tau = 2 x (tf32 truncation of both
-            // operands on 2M: 2*2^-9*S, fp32 accumulation + the canonical formula's own rounding, the index packing:
-            // 2^-(23-nbits) of |s| <= Emax^2 + 2S), with margin.
+            // operands on 2M: 2*2^-9*S, fp32 accumulation + the canonical formula's own rounding), with margin.
             const float S = sqrtf(A) * 1.00002f * Emax;
-            const float pack_eps = __int_as_float((127 - (23 - p.nbits)) << 23);       // 2^-(23-nbits)
-            const float tau = S * (0.0078125f + 0.0009765625f) + (A + Emax * Emax + S) * 1.9073486e-6f +
-                              2.f * pack_eps * (Emax * Emax + 2.f * S) * 1.01f + 1e-30f;
+            const float tau = S * (0.0078125f + 0.0009765625f) + (A + Emax * Emax + S) * 1.9073486e-6f + 1e-30f;
             const bool slow_row = bad_codebook || !(A < INF) || !(tau < INF) || !(rowmin == rowmin);
             const float thr = rowmin + tau;
             ptx::named_bar_sync(1 + q, 64);               // xch is reused by the next tile
 
-            // ---- this half's candidates: tracker minima inside the window; a tracker with TWO codes inside it may
-            // hide a third -> the row needs the whole-codebook scan ----
-            int n = 0;
-            bool needfull = slow_row;
-            int ids[MAXC];
-#pragma unroll
-            for (int i = 0; i < MAXC; ++i) ids[i] = 0;
+            // ---- this half's grid: the classes of every partition whose minimum is inside the window ----
+            unsigned R = 0u, Bm = 0u, Cm = 1u, Qm = 1u;
 #pragma unroll
             for (int i = 0; i < NTRK; ++i) {
-                if (m1[i] <= thr) {
-                    const uint32_t pos = __float_as_uint(m1[i]) & ~keep;          // chunk * 128 + position in the half
-                    const int k = (int)((pos >> 7) * CN + (uint32_t)(h * 128) + (pos & 127u));
-                    if (k >= p.K) needfull = true;                                 // (a padding column: only when every score is +inf)
-                    if (n < MAXC) {
-#pragma unroll
-                        for (int s = 0; s < MAXC; ++s) if (s == n) ids[s] = k;
-                    } else needfull = true;
-                    ++n;
-                }
-                if (m2[i] <= thr) needfull = true;
+                R |= m1[i] <= thr ? (1u << i) : 0u;
+                Bm |= mb[i] <= thr ? (1u << i) : 0u;
             }
+            if (!resident) {
+                Cm = 0u; Qm = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Cm |= mc[i] <= thr ? (1u << i) : 0u;
+                Qm = (m4[0] <= thr ? 1u : 0u) | (m4[1] <= thr ? 2u : 0u);
+            }
+            const int n = __popc(R) * __popc(Bm) * __popc(Cm) * __popc(Qm);
+            const bool needfull = slow_row || n > GCAP;
             const int par = it & 1;
             ptx::mbar_wait_sleep(bar(C_EMPTY + par), (uint32_t)(((it >> 1) & 1) ^ 1), 100);       // finish warps are done with tile it-2's records
-            int *rec = cand + (par * 256 + et) * 4;
-            rec[0] = needfull ? -1 : n;
-#pragma unroll
-            for (int s = 0; s < MAXC; ++s) rec[1 + s] = ids[s];
+            *reinterpret_cast<int4 *>(cand + (par * 256 + et) * 4) = make_int4(needfull ? -1 : n, (int)(R | (Bm << 16)), (int)(Cm | (Qm << 8)), 0);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(C_FULL + par));
         }
@@ -415,21 +437,37 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             unsigned char *zrow = ztile + row * 128;
             ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 200);
             ptx::mbar_wait_sleep(bar(C_FULL + par), (uint32_t)((it >> 1) & 1), 200);
-            const int *r0 = cand + (par * 256 + row) * 4, *r1 = cand + (par * 256 + 128 + row) * 4;
-            const int n0 = r0[0], n1 = r1[0];
+            const int4 g0 = *reinterpret_cast<const int4 *>(cand + (par * 256 + row) * 4);
+            const int4 g1 = *reinterpret_cast<const int4 *>(cand + (par * 256 + 128 + row) * 4);
+            const int n0 = g0.x, n1 = g1.x;
+            // grid point (i, b, c, q) of column half hh -> code: chunk pair 8 q + c, chunk (b >> 3), 16-column block b & 7, residue i
+            auto for_grid = [&](const int4 g, const int hh, auto &&f) {
+                for (unsigned qm = ((unsigned)g.z >> 8) & 3u; qm; qm &= qm - 1u)
+                    for (unsigned cm = (unsigned)g.z & 0xffu; cm; cm &= cm - 1u)
+                        for (unsigned bm = (unsigned)g.y >> 16; bm; bm &= bm - 1u)
+                            for (unsigned rm = (unsigned)g.y & 0xffffu; rm; rm &= rm - 1u) {
+                                const int qi = __ffs((int)qm) - 1, ci = __ffs((int)cm) - 1, bi = __ffs((int)bm) - 1, ri = __ffs((int)rm) - 1;
+                                f(((qi * 8 + ci) * 2 + (bi >> 3)) * CN + hh * 128 + (bi & 7) * 16 + ri);
+                            }
+            };
             int bk = -1, pbase = -1;
             float bd = 0.f;
             const int ncand = n0 + n1;
             bool queued = n0 < 0 || n1 < 0;
             if (!queued && ncand == 1) {
-                bk = n0 == 1 ? r0[1] : r1[1];            // the only code inside the window: provably the canonical argmin
+                // the only grid point: it holds the window's only code, provably the canonical argmin
+                if (n0 == 1) for_grid(g0, 0, [&](int k) { bk = k; });
+                else for_grid(g1, 1, [&](int k) { bk = k; });
+                if (bk >= p.K) { bk = -1; queued = true; }
             } else if (!queued) {
-                // 2..10 candidates: their (row, code) pairs join the tile's work list, re-scored densely below
+                // a few grid points: their (row, code) pairs join the tile's work list, re-scored densely below
                 pbase = atomicAdd(const_cast<int *>(&fq[135]), ncand);
                 if (pbase + ncand > PCAP) { queued = true; pbase = -1; }
                 else {
-                    for (int s2 = 0; s2 < n0; ++s2) prk[pbase + s2] = make_int2(row, r0[1 + s2]);
-                    for (int s2 = 0; s2 < n1; ++s2) prk[pbase + n0 + s2] = make_int2(row, r1[1 + s2]);
+                    int w = pbase;
+                    auto push = [&](int k) { prk[w++] = make_int2(row, k < p.K ? k : -1); };
+                    if (n0 > 0) for_grid(g0, 0, push);
+                    if (n1 > 0) for_grid(g1, 1, push);
                 }
             }
             if (queued) {
@@ -441,7 +479,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 const int np = min((int)fq[135], PCAP);
                 for (int pi = ft; pi < np; pi += 128) {
                     const int2 rk = prk[pi];
-                    pdist[pi] = exact_dist(ztile + rk.x * 128, rk.x & 7, rk.y);
+                    if (rk.y >= 0) pdist[pi] = exact_dist(ztile + rk.x * 128, rk.x & 7, rk.y);
                 }
             }
             const int nq = fq[0];
@@ -476,7 +514,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 for (int s2 = 0; s2 < ncand; ++s2) {
                     const int k = prk[pbase + s2].y;
                     const float dist = pdist[pbase + s2];
-                    if (k < p.K && (bk < 0 || vq2_better(dist, k, bd, bk))) { bd = dist; bk = k; }
+                    if (k >= 0 && (bk < 0 || vq2_better(dist, k, bd, bk))) { bd = dist; bk = k; }
                 }
             }
             if (ft == 0) { fq[0] = 0; fq[135] = 0; }      // this parity's counters are next used two tiles (>= two barriers) later
@@ -508,7 +546,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 if (p.zq_bf16) {
                     // bf16 rows (128 B) over the first atom: piece c8 holds channels 8 c8 .. 8 c8 + 7.  It overwrites fp32 piece
                     // c8 of atom 0 (channels 4 c8 ..), which this thread has already consumed (pieces are read in order 2 c8, 2 c8 + 1
-                    // >= c8) -- except nothing: piece index c8 <= 2 c8 always.
+                    // >= c8).
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
                     *reinterpret_cast<uint4 *>(zrow + ((c8 ^ rsw) << 4)) =
@@ -591,7 +629,9 @@ int launch_vq2(const float *z, const float *E, long long N, int K, int D, long l
     }
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(vq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        e = cudaFuncSetAttribute(vq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(vq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -604,11 +644,12 @@ int launch_vq2(const float *z, const float *E, long long N, int K, int D, long l
     Vq2Params p;
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
-    p.nbits = 7;
-    while ((1 << p.nbits) < nchunks * 128) ++p.nbits;       // position of a code inside one thread's half: chunk * 128 + column
+    p.nbits = 0;
     p.idx = idx; p.partials = partials; p.hist = hist; p.zq_bf16 = zq_bf16;
     p.pending = reinterpret_cast<unsigned *>(w + vq_ws_marker_offset(K));
-    if (cudaError_t le = vqb_launch(vq2_kernel, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)) return (int)le;
+    if (cudaError_t le = nchunks <= 2 ? vqb_launch(vq2_kernel<true>, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)
+                                      : vqb_launch(vq2_kernel<false>, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p))
+        return (int)le;
     if (!defer) vq_tc_sum(partials, grid, sse, s);
     VQB_COUNT_LAUNCH(defer ? nlaunch - 1 : nlaunch);
     return vqb_cuda_status(cudaGetLastError());
