@@ -68,7 +68,10 @@ BF16_LAYER_CASES = [
     (5, 128, 8, 8, 64, 1, 1, False, False, True),       # cfg2 size, ragged batch (5 images, 2 per tile)
     (2, 64, 32, 32, 3, 4, 2, True, False, True),        # decoder.py:34-35 -> fp32 NCHW, pixel shuffle
     (1, 64, 128, 128, 3, 4, 2, True, False, True),      # cfg3 size
-    (3, 64, 16, 16, 3, 4, 2, True, True, True),         # cfg2 size
+    (3, 64, 16, 16, 3, 4, 2, True, True, True),         # cfg2 size (ReLU asked: the gather-form kernel)
+    (2, 64, 20, 37, 3, 4, 2, True, False, True),        # scatter form (convt_out_bf16.cu), ragged 14x14 interiors, odd width
+    (5, 64, 14, 14, 3, 4, 2, True, False, True),        # one exact tile per image
+    (3, 64, 15, 29, 3, 4, 2, True, False, True),        # one-pixel remainders
     (1, 64, 12, 20, 48, 3, 1, False, True, False),      # Cout = 48 (16-column tail group), ragged
     (1, 256, 16, 16, 64, 3, 1, False, False, False),    # four 64-channel chunks
 ]

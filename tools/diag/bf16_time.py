@@ -23,14 +23,14 @@ def t(fn, n=10):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-def layer(name, Cin, H, W, Cout, k, stride, transposed, out_f32=False):
+def layer(name, Cin, H, W, Cout, k, stride, transposed, out_f32=False, relu=True):
     x = (torch.randn((B, H, W, Cin), device=dev, generator=g)).to(torch.bfloat16)
     wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
     w = torch.randn(wshape, device=dev, generator=g) / np.sqrt(Cin * k * k)
     b = torch.randn((Cout,), device=dev, generator=g) * 0.1
     kind = ops.conv_kind(k, stride, transposed, Cout)
     pk = ops.pack_conv_weight_bf16(w, kind)
-    us = t(lambda: ops.conv2d_bf16(x, pk, b, B=B, Cin=Cin, H=H, W=W, Cout=Cout, kind=kind, relu=True, out_f32=out_f32))
+    us = t(lambda: ops.conv2d_bf16(x, pk, b, B=B, Cin=Cin, H=H, W=W, Cout=Cout, kind=kind, relu=relu, out_f32=out_f32))
     macs = B * H * W * Cin * Cout * k * k if transposed else B * (H // stride) * (W // stride) * Cin * Cout * k * k
     print(f"{name:28s} {us:9.1f} us   {2 * macs / us / 1e6:8.1f} TFLOP/s", flush=True)
 
@@ -41,7 +41,8 @@ layer("E3 conv 128->128 k3", 128, L, L, 128, 3, 1, False)
 layer("pre 1x1 128->64 (f32 out)", 128, L, L, 64, 1, 1, False, True)
 layer("D1 convT 64->128 k3", 64, L, L, 128, 3, 1, True)
 layer("D2 convT 128->64 k4s2", 128, L, L, 64, 4, 2, True)
-layer("D3 convT 64->3 k4s2", 64, S // 2, S // 2, 3, 4, 2, True, True)
+layer("D3 convT 64->3 k4s2 (gather form)", 64, S // 2, S // 2, 3, 4, 2, True, True)
+layer("D3 convT 64->3 k4s2 (scatter form)", 64, S // 2, S // 2, 3, 4, 2, True, True, relu=False)
 r = torch.randn((B, L, L, 128), device=dev, generator=g).clamp_min(0).to(torch.bfloat16)
 w1 = torch.randn((32, 128, 3, 3), device=dev, generator=g) / np.sqrt(1152)
 w2 = torch.randn((128, 32, 1, 1), device=dev, generator=g) / np.sqrt(32)

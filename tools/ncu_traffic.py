@@ -43,17 +43,15 @@ flat = [(cfg, lab) for cfg in ("cfg2", "cfg3") for lab in labels.get(cfg, [])]
 if len(flat) != len(launches):
     sys.exit("label / launch count mismatch: %d labels, %d layer kernels: %s" % (len(flat), len(launches), [r[col["Kernel Name"]][:30] for r in launches]))
 acc, lines = {}, []
-lines.append("%-5s %-42s %-28s %9s %11s %11s %7s %7s %7s" % ("cfg", "bench label", "kernel", "us(ncu)", "dram rd MB", "dram wr MB", "dram%", "tensor%", "issue%"))
+lines.append("%-5s %-42s %-28s %9s %11s %11s %7s" % ("cfg", "bench label", "kernel", "us(ncu)", "dram rd MB", "dram wr MB", "issue%"))
 for (cfg, lab), r in zip(flat, launches):
     rd, wr = scaled(r, "dram__bytes_read.sum"), scaled(r, "dram__bytes_write.sum")
     t = scaled(r, "gpu__time_duration.sum")
     acc.setdefault(lab, []).append(rd + wr)
     g = lambda n: (r[col[n]] if n in col else "-")  # noqa: E731
-    lines.append("%-5s %-42s %-28s %9.1f %11.2f %11.2f %7s %7s %7s" % (
-        cfg, lab[:42], re.sub(r"\(.*", "", r[col["Kernel Name"]])[:28], t, rd / 1e6, wr / 1e6,
-        g("dram__throughput.avg.pct_of_peak_sustained_elapsed"), g("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed")
-        if "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed" in col else g("sm__inst_executed_pipe_tensor.sum"),
-        g("smsp__issue_active.avg.pct_of_peak_sustained_active")))
+    kn = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("void ", "").replace("<unnamed>::", "")
+    lines.append("%-5s %-42s %-28s %9.1f %11.2f %11.2f %7s" % (cfg, lab[:42], kn[:28], t, rd / 1e6, wr / 1e6,
+                                                            g("smsp__issue_active.avg.pct_of_peak_sustained_active")[:6]))
 json.dump({k: sum(v) / len(v) for k, v in acc.items()}, open(out_json, "w"), indent=1, sort_keys=True)
 open(out_txt, "w").write("# ncu --set full --clock-control none, one VQVAE.forward per configuration (tools/diag/step_once.py); times are\n"
                          "# cold-cache and serialised -- shares, not absolutes, compare with bench.py's live CUDA-event times.\n" + "\n".join(lines) + "\n")

@@ -35,6 +35,10 @@
 #include "ptx.cuh"
 #include "bf16_common.cuh"
 
+void convt_out_scatter_column(int n, int *co, int *ky, int *kx);
+int launch_convt_out_scatter(const void *in, const void *packed, int packed_rows, int w_row0, const float *bias, float *out, int B, int H,
+                             int W, cudaStream_t s);
+
 namespace {
 
 constexpr int HC_THREADS = 384;
@@ -366,6 +370,7 @@ struct Plan {
     PlanStep steps[2][HC_MAX_STEPS];
     int NCOL = 0, nbmax = 0, nbhalf = 0, halo = 1, epi_mode = EPI_NHWC, cg = 0, sy = 1, sx = 1, transposed = 0, s2d = 0;
     std::vector<RowDesc> rows;
+    int scatter_row0 = -1;          // VQB_CONVT_K4S2_OUT, Cin = 64, Cout = 3: first of the 64 GEMM-column rows of convt_out_bf16.cu
 };
 
 void add_step(Plan &pl, int pass, int chunk, int dy, int dx, int nb, int d_col, int w_row, bool half) {
@@ -467,6 +472,15 @@ bool build_plan(Plan &pl, int kind, int Cin, int Cout) {
                     add_step(pl, 0, k, dy, dx, 16, 0, row0, false);
                 }
             }
+            if (Cin == 64 && Cout == 3) {
+                // the same layer in scatter form (convt_out_bf16.cu): 64 more rows, one per GEMM column (ky, kx, co)
+                pl.scatter_row0 = (int)pl.rows.size();
+                for (int n = 0; n < 64; ++n) {
+                    int co, ky, kx;
+                    convt_out_scatter_column(n, &co, &ky, &kx);
+                    pl.rows.push_back({co, 0, ky, kx});
+                }
+            }
             break;
         }
         default: return false;
@@ -562,6 +576,8 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
     if (pl->s2d && ((H | W) & 1)) return VQB_ERR_UNSUPPORTED;
     if (kind == VQB_CONVT_K4S2_OUT) out_f32 = 1;
     cudaStream_t s = (cudaStream_t)stream;
+    if (kind == VQB_CONVT_K4S2_OUT && pl->scatter_row0 >= 0 && !relu)
+        return launch_convt_out_scatter(in, packed, (int)pl->rows.size(), pl->scatter_row0, bias, reinterpret_cast<float *>(out), B, H, W, s);
 
     HParams q;
     memset(&q, 0, sizeof(q));

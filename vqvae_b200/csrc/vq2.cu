@@ -32,6 +32,25 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#if VQB_DIAG
+// in-kernel timeline of CTA 0 (SM cycle counter), tools/diag/vq2_timeline.py; diagnostic builds only
+__device__ unsigned long long g_vq2_tl[32 * 32];
+extern "C" int vqb_debug_read_vq2_timeline(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 32 * 32) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_vq2_tl, sizeof(unsigned long long) * n));
+}
+#define VQ2_TL(it_, ev_)                                                                      \
+    do {                                                                                      \
+        if (blockIdx.x == 0 && (it_) >= 0 && (it_) < 32) {                                    \
+            unsigned long long t_;                                                            \
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_));                                \
+            g_vq2_tl[(it_) * 32 + (ev_)] = t_;                                                \
+        }                                                                                     \
+    } while (0)
+#else
+#define VQ2_TL(it_, ev_) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int TM = 128;          // latent rows per tile (UMMA M)
@@ -150,15 +169,18 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             auto drain = [&](int jt, long long jtile) {      // z_q of tile jt is complete in its z stage: store it
                 const int zs = jt & 1;
                 ptx::mbar_wait_sleep(bar(Q_DONE + zs), (jt >> 1) & 1, 100);
+                VQ2_TL(jt, 1);
                 const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
                 tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
                 if (!p.zq_bf16) tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
                 bulk_commit();
                 bulk_wait_read0();
+                VQ2_TL(jt, 2);
             };
             for (; tile < ntiles; tile += gridDim.x, ++it) {
                 const int zs = it & 1;
                 if (it >= 2) drain(it - 2, tile - 2 * (long long)gridDim.x);
+                VQ2_TL(it, 0);
                 ptx::mbar_expect_tx(bar(Z_FULL + zs), ZSTAGE);
                 const uint32_t zdst = sbase + OFF_Z + zs * ZSTAGE;
                 ptx::tma_load_2d(zdst, &tmz, bar(Z_FULL + zs), 0, (int)(tile * TM));
@@ -189,6 +211,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1;
             ptx::mbar_wait(bar(Z_FULL + zs), (it >> 1) & 1);
+            if (leader) VQ2_TL(it, 3);
             const uint32_t za_lo = (sbase + OFF_Z + zs * ZSTAGE) >> 4;
             for (int c = 0; c < nchunks; ++c) {
                 const long long gc = (long long)it * nchunks + c;
@@ -203,6 +226,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 const int ab = (int)(gc & 1);
                 ptx::mbar_wait(bar(T_EMPTY + ab), (uint32_t)(((gc >> 1) & 1) ^ 1));
                 ptx::tc_fence_after();
+                if (leader && c < 2) VQ2_TL(it, 4 + 2 * c);
                 const uint32_t ea_lo = (sbase + OFF_E + es * ESTAGE) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < DD / 8; ++ks)
@@ -210,6 +234,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                         ptx::mma_tf32_w(tmem_base + ab * CN, za_lo + (ks >> 2) * (ZATOM >> 4) + (ks & 3) * 2, d_hi,
                                         ea_lo + (ks >> 2) * (EATOM >> 4) + (ks & 3) * 2, d_hi, idesc, ks > 0 ? 1u : 0u);
                 if (leader) {
+                    if (c < 2) VQ2_TL(it, 5 + 2 * c);
                     ptx::tc_commit(bar(T_FULL + ab));
                     if (!resident) ptx::tc_commit(bar(E_EMPTY + es));
                 }
@@ -272,6 +297,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             const int zs = it & 1;
             const unsigned char *zrow = sm + OFF_Z + zs * ZSTAGE + row * 128;
             ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 100);
+            if (tid == 128) VQ2_TL(it, 8);
             // this thread's half of ||z||^2 (any order: it only feeds the error bound tau)
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -300,6 +326,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                         const int es = resident ? c : (int)(gc & 1);
                         ptx::mbar_wait_sleep(bar(T_FULL + ab), (uint32_t)((gc >> 1) & 1), 64);
                         ptx::tc_fence_after();
+                        if (tid == 128 && c < 2) VQ2_TL(it, 9 + 2 * c);
                         const float *bch = bsm + es * CN + h * 128;
                         const uint32_t tcol = lane_taddr + (uint32_t)(ab * CN + h * 128);
                         float va[32], vb[32];
@@ -347,6 +374,8 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                         process(vb, 3);
                         ptx::tc_fence_before();
                         __syncwarp();
+                        if (tid == 128 && c < 2) VQ2_TL(it, 10 + 2 * c);
+                        if (tid == 352 && c < 2) VQ2_TL(it, 16 + c);
                         if (lane == 0) {
                             ptx::mbar_arrive(bar(T_EMPTY + ab));
                             if (!resident) ptx::mbar_arrive(bar(E_EMPTY + es));
@@ -382,6 +411,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             const bool slow_row = bad_codebook || !(A < INF) || !(tau < INF) || !(rowmin == rowmin);
             const float thr = rowmin + tau;
             ptx::named_bar_sync(1 + q, 64);               // xch is reused by the next tile
+            if (tid == 128) VQ2_TL(it, 13);
 
             // ---- this half's grid: the classes of every partition whose minimum is inside the window ----
             unsigned R = 0u, Bm = 0u, Cm = 1u, Qm = 1u;
@@ -400,9 +430,11 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             const bool needfull = slow_row || n > GCAP;
             const int par = it & 1;
             ptx::mbar_wait_sleep(bar(C_EMPTY + par), (uint32_t)(((it >> 1) & 1) ^ 1), 100);       // finish warps are done with tile it-2's records
+            if (tid == 128) VQ2_TL(it, 14);
             *reinterpret_cast<int4 *>(cand + (par * 256 + et) * 4) = make_int4(needfull ? -1 : n, (int)(R | (Bm << 16)), (int)(Cm | (Qm << 8)), 0);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(C_FULL + par));
+            if (tid == 128) VQ2_TL(it, 15);
         }
     } else if (warp >= 12) {
         // ===================== finish warps: thread = row =====================
@@ -437,6 +469,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             unsigned char *zrow = ztile + row * 128;
             ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 200);
             ptx::mbar_wait_sleep(bar(C_FULL + par), (uint32_t)((it >> 1) & 1), 200);
+            if (ft == 0) VQ2_TL(it, 20);
             const int4 g0 = *reinterpret_cast<const int4 *>(cand + (par * 256 + row) * 4);
             const int4 g1 = *reinterpret_cast<const int4 *>(cand + (par * 256 + 128 + row) * 4);
             const int n0 = g0.x, n1 = g1.x;
@@ -475,6 +508,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 fq[1 + slot] = row;
             }
             ptx::named_bar_sync(6, 128);                   // work list and queue are complete
+            if (ft == 0) VQ2_TL(it, 21);
             {
                 const int np = min((int)fq[135], PCAP);
                 for (int pi = ft; pi < np; pi += 128) {
@@ -482,6 +516,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                     if (rk.y >= 0) pdist[pi] = exact_dist(ztile + rk.x * 128, rk.x & 7, rk.y);
                 }
             }
+            if (ft == 0) VQ2_TL(it, 22);
             const int nq = fq[0];
             // whole-codebook exact scans, all 128 finish threads per queued row: thread t takes codes t, t+128, ...
             for (int qi = 0; qi < nq; ++qi) {
@@ -510,6 +545,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                 if ((qi & 7) == 7) ptx::named_bar_sync(6, 128);      // the 8 partial slots are recycled
             }
             ptx::named_bar_sync(6, 128);                   // pair distances (and queue results) are complete
+            if (ft == 0) VQ2_TL(it, 23);
             if (pbase >= 0) {
                 for (int s2 = 0; s2 < ncand; ++s2) {
                     const int k = prk[pbase + s2].y;
@@ -562,6 +598,8 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             }
             ptx::fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
             __syncwarp();
+            if (ft == 0) VQ2_TL(it, 24);
+            if (ft == 96) VQ2_TL(it, 25);
             if (lane == 0) { ptx::mbar_arrive(bar(Q_DONE + zs)); ptx::mbar_arrive(bar(C_EMPTY + par)); }
         }
         // ---- CTA reduction of the SSE partial, histogram flush ----
