@@ -539,6 +539,11 @@ def main():
         line_extra["fp32_mode"] = {"value": m["value"], "unit": "images/sec", "ms_per_step": m["ms_per_step"], "dtype": "f32",
                                    "gpu_launches": m["launches"], "kernels": m.get("kernels", [])[:8], "flips": m.get("flips"),
                                    "note": "same workload with every conv in fp32 FFMA (CUDA cores): the CPU reference's numerics"}
+        mb = run_mode("bf16", False)
+        line_extra["bf16_mode"] = {"value": mb["value"], "unit": "images/sec", "ms_per_step": mb["ms_per_step"], "dtype": "bf16",
+                                   "gpu_launches": mb["launches"], "kernels": mb.get("kernels", [])[:12], "flips": mb.get("flips"),
+                                   "note": "same workload through the bf16 pipeline (tcgen05 kind::f16 on bf16 operands, bf16 NHWC "
+                                           "activations, exact fp32 VQ): the arithmetic of the reference under torch.autocast(bfloat16)"}
         vqvae_b200.set_precision(prec_main)
 
     # ---- shard parity (N > 1): rank 0's shard inside the sharded job == the same images through a single-process forward

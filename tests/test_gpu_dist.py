@@ -20,7 +20,7 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
-    from oracle.weights import make_images, make_state_dict
+    from vqvae_b200.synth import make_images, make_state_dict
     from tests.helpers import build_model
     from vqvae_b200.dist import shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,8 +36,15 @@ def _worker(rank, world, port, out_dir):
     loss, x_hat, perp = m(torch.from_numpy(x[lo:hi]).cuda())
     idx = m.last_min_encoding_indices
     torch.cuda.synchronize()
+    # lazy scalars: no collective inside the forward, whole-batch values on demand
+    m.sync_scalars = False
+    loss_l, x_hat_l, perp_l = m(torch.from_numpy(x[lo:hi]).cuda())
+    loss_r, perp_r = m.reduce_scalars()
+    m.sync_scalars = True
+    torch.cuda.synchronize()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss.cpu().numpy(), perp=perp.cpu().numpy(),
-             x_hat=x_hat.cpu().numpy(), idx=idx.cpu().numpy())
+             x_hat=x_hat.cpu().numpy(), idx=idx.cpu().numpy(), loss_local=loss_l.cpu().numpy(), perp_local=perp_l.cpu().numpy(),
+             loss_reduced=loss_r.cpu().numpy(), perp_reduced=perp_r.cpu().numpy(), x_hat_lazy=x_hat_l.cpu().numpy())
     if rank == 0:
         m.process_group = None
         loss1, x_hat1, perp1 = m(torch.from_numpy(x).cuda())
@@ -59,3 +66,9 @@ def test_two_gpu_shards_equal_single_process(tmp_path):
     for r in (r0, r1):
         np.testing.assert_allclose(r["loss"], one["loss"], rtol=1e-6)
         np.testing.assert_allclose(r["perp"], one["perp"], rtol=1e-6)
+        # sync_scalars = False: the forward returns the shard's own scalars (no collective), reduce_scalars() the whole batch's
+        np.testing.assert_allclose(r["loss_reduced"], one["loss"], rtol=1e-6)
+        np.testing.assert_allclose(r["perp_reduced"], one["perp"], rtol=1e-6)
+        assert np.array_equal(r["x_hat_lazy"], r["x_hat"])
+    np.testing.assert_allclose(0.5 * (r0["loss_local"] + r1["loss_local"]), one["loss"], rtol=1e-6)   # equal shards: the mean of means
+    assert not np.allclose(r0["perp_local"], r1["perp_local"], rtol=1e-9)                            # really per-shard values

@@ -26,6 +26,7 @@ constexpr int CIB_THREADS = 512;
 constexpr int COUT = 64;
 constexpr uint32_t A_BYTES = 2 * 16384;                 // two K atoms x [128 rows][128 B]
 constexpr uint32_t B_ATOM = COUT * 128;
+constexpr int NA = 3;                                   // im2col tiles / TMEM accumulators / staging tiles in flight
 constexpr int NRAW = 4;                                 // staged-input buffers: the TMA loads run three tiles ahead (HBM round trip)
 
 struct CibParams {
@@ -49,33 +50,33 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (sbase - raw);
     // [A x2][B: 2 atoms][staging 16 KB][raw rows x2][barriers, bias]
-    const uint32_t b_off = 2 * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + 2 * 16384u;      // (two staging tiles)
+    const uint32_t b_off = NA * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + NA * 16384u;
     const uint32_t raw_stride = ((uint32_t)p.raw_bytes + 127u) & ~127u;
     const uint32_t bar_off = raw_off + NRAW * raw_stride;
     const uint32_t bars = sbase + bar_off;
     auto rfull = [&](int s) { return bars + 8u * s; };
     auto rempty = [&](int s) { return bars + 8u * (NRAW + s); };
     auto afull = [&](int s) { return bars + 8u * (2 * NRAW + s); };
-    auto aempty = [&](int s) { return bars + 8u * (2 * NRAW + 2 + s); };
-    auto tfull = [&](int s) { return bars + 8u * (2 * NRAW + 4 + s); };
-    auto tempty = [&](int s) { return bars + 8u * (2 * NRAW + 6 + s); };
-    auto sfree = [&](int s) { return bars + 8u * (2 * NRAW + 8 + s); };
-    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 10));
-    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 12));
+    auto aempty = [&](int s) { return bars + 8u * (2 * NRAW + NA + s); };
+    auto tfull = [&](int s) { return bars + 8u * (2 * NRAW + 2 * NA + s); };
+    auto tempty = [&](int s) { return bars + 8u * (2 * NRAW + 3 * NA + s); };
+    auto sfree = [&](int s) { return bars + 8u * (2 * NRAW + 4 * NA + s); };
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 5 * NA));
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 5 * NA + 2));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, W = p.W, OW = W / 2, OH = H / 2, R = p.R, NR = 2 * R + 2;
     if (tid == 0) {
         for (int s = 0; s < NRAW; ++s) { ptx::mbar_init(rfull(s), 1); ptx::mbar_init(rempty(s), 8); }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NA; ++s) {
             ptx::mbar_init(afull(s), 8); ptx::mbar_init(aempty(s), 1);
             ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4);
         }
-        ptx::mbar_init(sfree(0), 1); ptx::mbar_init(sfree(1), 1);
+        for (int s = 0; s < NA; ++s) ptx::mbar_init(sfree(s), 1);
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tma_x); ptx::prefetch_tmap(&tma_out);
     }
-    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * NRAW + 10), 128);
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * NRAW + 5 * NA), 256);
     for (int c = tid; c < COUT; c += CIB_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
     // ---- B operand, once per CTA: wp[k][co] (k = (r*4+s)*3 + c, 48 rows) -> K-major swizzled rows ----
     for (int i = tid; i < COUT * 12; i += CIB_THREADS) {
@@ -115,9 +116,9 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         constexpr uint32_t idesc = ptx::instr_desc(ptx::FMT_TF32, 128, COUT);
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-            const int s = it & 1;
-            ptx::mbar_wait(afull(s), (uint32_t)((it >> 1) & 1));
-            ptx::mbar_wait(tempty(s), (uint32_t)(((it >> 1) & 1) ^ 1));
+            const int s = it % NA;
+            ptx::mbar_wait(afull(s), (uint32_t)((it / NA) & 1));
+            ptx::mbar_wait(tempty(s), (uint32_t)(((it / NA) & 1) ^ 1));
             ptx::tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks)       // K = 48: four k-steps of atom 0, two of atom 1
@@ -135,9 +136,9 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         int it = 0;
         uint32_t rs = 0, rpar = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-            const int s = it & 1;
+            const int s = it % NA;
             ptx::mbar_wait_sleep(rfull((int)rs), rpar, 32);
-            ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1), 32);
+            ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it / NA) & 1) ^ 1), 32);
             const float *rawp = reinterpret_cast<const float *>(sm + raw_off + rs * raw_stride);
             float v[24];                                          // k_local = (trl*4 + s)*3 + c
 #pragma unroll
@@ -171,8 +172,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         const bool storer = tid == 384;
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-            const int s = it & 1;
-            ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it >> 1) & 1), 32);
+            const int s = it % NA;
+            ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it / NA) & 1), 32);
             ptx::tc_fence_after();
             float va[32], vb[32];
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * COUT);
@@ -184,7 +185,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty(s));          // the accumulator is in registers
             unsigned char *orow = sm + st_off + s * 16384 + row * 128;
-            ptx::mbar_wait(sfree(s), (uint32_t)(((it >> 1) & 1) ^ 1));       // the store of tile it-2 has read this staging buffer
+            ptx::mbar_wait(sfree(s), (uint32_t)(((it / NA) & 1) ^ 1));       // the store of tile it-2 has read this staging buffer
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -207,15 +208,16 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
                                  "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + st_off + (uint32_t)s * 16384u), "r"(0), "r"((int)(tile * 128)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                ptx::mbar_arrive(sfree(s));
+                // release the staging tile of store it-(NA-1): this thread never waits for the store it has just issued
+                asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(NA - 1) : "memory");
+                if (it >= NA - 1) ptx::mbar_arrive(sfree((it - (NA - 1)) % NA));
             }
         }
         if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, 128);
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace
@@ -251,7 +253,7 @@ int launch_conv_in_bf16_persistent(const float *x, const float *wp, const float 
         if (rc) return rc;
     }
     const int raw_stride = (q.raw_bytes + 127) & ~127;
-    const int smem = 2 * (int)A_BYTES + 2 * (int)B_ATOM + 2 * 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 12) + COUT * 4 + 1024;
+    const int smem = NA * (int)A_BYTES + 2 * (int)B_ATOM + NA * 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 5 * NA + 2) + COUT * 4 + 1024;
     if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
     static int attr_max = 0;
     if (smem > attr_max) {

@@ -68,11 +68,12 @@ constexpr int OFF_E = OFF_Z + 2 * ZSTAGE;
 constexpr int OFF_B = OFF_E + 2 * ESTAGE;                    // float[2 * CN]
 constexpr int OFF_CAND = OFF_B + 2 * CN * 4;                 // 2 tiles x 256 half rows x int4 (grid size or -1, R | B << 16, C | Q << 8, 0)
 constexpr int OFF_XCH = OFF_CAND + 2 * 256 * 16;             // float2[256]: (half-row min, partial ||z||^2)
-constexpr int PCAP = 1024;                                   // (row, code) pairs re-scored per tile (typically ~100)
+constexpr int PCAP = 512;                                    // (row, code) pairs re-scored per tile (typically 100-250); one list per tile parity:
+                                                             // a warp may push tile t+1's pairs while another still reads tile t's distances
 constexpr int OFF_Q = OFF_XCH + 256 * 8;                     // per tile parity: int[136] = full-scan queue (count + rows) + pair count
 constexpr int OFF_QR = OFF_Q + 2 * 136 * 4;                  // per finish warp (d, k) partials: 4 x (float,int) x 8 slots
 constexpr int OFF_PAIR = OFF_QR + 4 * 8 * 8;                 // pairs: int2 (row, k)[PCAP] then float dist[PCAP]
-constexpr int OFF_HIST = OFF_PAIR + PCAP * 12;
+constexpr int OFF_HIST = OFF_PAIR + 2 * PCAP * 12;
 constexpr int OFF_BAR = OFF_HIST + HIST_MAX * 4;
 constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
 constexpr int OFF_RED = OFF_TMEM + 64;
@@ -93,6 +94,7 @@ struct Vq2Params {
     unsigned *pending;
     int *hist;
     int zq_bf16;
+    void *zq;              // (N, 64) fp32 or bf16 rows
 };
 
 __device__ __forceinline__ bool vq2_better(float dn, int kn, float db, int kb) {
@@ -100,18 +102,10 @@ __device__ __forceinline__ bool vq2_better(float dn, int kn, float db, int kb) {
     if (nn || nb) return nn && (!nb || kn < kb);
     return dn < db || (dn == db && kn < kb);
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
-                     "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-template <bool RESIDENT>
+template <bool RESIDENT, bool ZQBF>
 __global__ void __launch_bounds__(NT2, 1)
 vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUtensorMap tme,
-           const __grid_constant__ CUtensorMap tmq, const Vq2Params p) {
+           const Vq2Params p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = ptx::smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -134,7 +128,7 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
     const float INF = __int_as_float(0x7f800000);
 
     if (tid == 0) {
-        ptx::prefetch_tmap(&tmz); ptx::prefetch_tmap(&tme); ptx::prefetch_tmap(&tmq);
+        ptx::prefetch_tmap(&tmz); ptx::prefetch_tmap(&tme);
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(bar(Z_FULL + s), 1);
             ptx::mbar_init(bar(Q_DONE + s), 4);       // 4 finish warps
@@ -166,20 +160,12 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             long long gc = 0;
             int it = 0;
             long long tile = blockIdx.x;
-            auto drain = [&](int jt, long long jtile) {      // z_q of tile jt is complete in its z stage: store it
-                const int zs = jt & 1;
-                ptx::mbar_wait_sleep(bar(Q_DONE + zs), (jt >> 1) & 1, 100);
-                VQ2_TL(jt, 1);
-                const uint32_t src = sbase + OFF_Z + zs * ZSTAGE;
-                tma_store_2d(&tmq, src, 0, (int)(jtile * TM));
-                if (!p.zq_bf16) tma_store_2d(&tmq, src + ZATOM, 32, (int)(jtile * TM));
-                bulk_commit();
-                bulk_wait_read0();
-                VQ2_TL(jt, 2);
-            };
             for (; tile < ntiles; tile += gridDim.x, ++it) {
                 const int zs = it & 1;
-                if (it >= 2) drain(it - 2, tile - 2 * (long long)gridDim.x);
+                if (it >= 2) {                   // the finish warps have emitted tile it-2 from this stage
+                    ptx::mbar_wait_sleep(bar(Q_DONE + zs), (uint32_t)(((it - 2) >> 1) & 1), 32);
+                    VQ2_TL(it - 2, 1);
+                }
                 VQ2_TL(it, 0);
                 ptx::mbar_expect_tx(bar(Z_FULL + zs), ZSTAGE);
                 const uint32_t zdst = sbase + OFF_Z + zs * ZSTAGE;
@@ -198,9 +184,6 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
                         ptx::bulk_load_1d(sbase + OFF_B + es * CN * 4, p.bn + (size_t)c * CN, CN * 4, bar(E_FULL + es));
                 }
             }
-            for (int jt = (it >= 2 ? it - 2 : 0); jt < it; ++jt)
-                drain(jt, (long long)blockIdx.x + (long long)jt * gridDim.x);
-            bulk_wait_all0();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (converged warp, elected leader lane issues) =====================
@@ -439,11 +422,13 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
     } else if (warp >= 12) {
         // ===================== finish warps: thread = row =====================
         const int ft = tid - 384;               // 0..127 = row of the tile
-        const int row = ft, rsw = row & 7;
+        const int row = ft;
         double sse = 0.0;
         float *qr = reinterpret_cast<float *>(sm + OFF_QR);
-        int2 *prk = reinterpret_cast<int2 *>(sm + OFF_PAIR);
-        float *pdist = reinterpret_cast<float *>(sm + OFF_PAIR + PCAP * 8);
+        int2 *prk_all = reinterpret_cast<int2 *>(sm + OFF_PAIR);
+        float *pdist_all = reinterpret_cast<float *>(sm + OFF_PAIR + 2 * PCAP * 8);
+        for (int i = ft; i < 2 * PCAP; i += 128) prk_all[i] = make_int2(0, -1);      // slots a list overflow leaves unwritten must stay harmless
+        ptx::named_bar_sync(6, 128);
         // canonical distance of code k to the z row at `zr_s` (shared memory, swizzled): A = sum fl(z^2) left to right,
         // M = one sequential fmaf chain, d = fl(fl(A + B_k) - fl(2 M))   (quantizer.py:49-51, oracle.c)
         auto exact_dist = [&](const unsigned char *zr_s, int zsw, int k) -> float {
@@ -461,14 +446,38 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             const float bnk = resident ? bsm[k] : __ldg(p.bn + k);
             return __fsub_rn(__fadd_rn(A, bnk), __fmul_rn(2.0f, M));
         };
+        auto exact_dist2 = [&](const unsigned char *za, int zswa, int ka, const unsigned char *zb, int zswb, int kb, float &da, float &db) {
+            float Aa = 0.f, Ma = 0.f, Ab = 0.f, Mb = 0.f;
+            const unsigned char *esa = code_ptr_smem(ka), *esb = code_ptr_smem(kb);
+            const float4 *ega = reinterpret_cast<const float4 *>(p.E + (size_t)ka * DD), *egb = reinterpret_cast<const float4 *>(p.E + (size_t)kb * DD);
+#pragma unroll
+            for (int c16 = 0; c16 < 16; ++c16) {
+                const float4 va = *reinterpret_cast<const float4 *>(za + (c16 >> 3) * ZATOM + (((c16 & 7) ^ zswa) << 4));
+                const float4 vb = *reinterpret_cast<const float4 *>(zb + (c16 >> 3) * ZATOM + (((c16 & 7) ^ zswb) << 4));
+                const float4 ea = resident ? *reinterpret_cast<const float4 *>(esa + (c16 >> 3) * EATOM + (((c16 & 7) ^ (ka & 7)) << 4)) : __ldg(ega + c16);
+                const float4 eb = resident ? *reinterpret_cast<const float4 *>(esb + (c16 >> 3) * EATOM + (((c16 & 7) ^ (kb & 7)) << 4)) : __ldg(egb + c16);
+                Aa = __fadd_rn(Aa, __fmul_rn(va.x, va.x)); Ab = __fadd_rn(Ab, __fmul_rn(vb.x, vb.x));
+                Aa = __fadd_rn(Aa, __fmul_rn(va.y, va.y)); Ab = __fadd_rn(Ab, __fmul_rn(vb.y, vb.y));
+                Aa = __fadd_rn(Aa, __fmul_rn(va.z, va.z)); Ab = __fadd_rn(Ab, __fmul_rn(vb.z, vb.z));
+                Aa = __fadd_rn(Aa, __fmul_rn(va.w, va.w)); Ab = __fadd_rn(Ab, __fmul_rn(vb.w, vb.w));
+                Ma = __fmaf_rn(va.x, ea.x, Ma); Mb = __fmaf_rn(vb.x, eb.x, Mb);
+                Ma = __fmaf_rn(va.y, ea.y, Ma); Mb = __fmaf_rn(vb.y, eb.y, Mb);
+                Ma = __fmaf_rn(va.z, ea.z, Ma); Mb = __fmaf_rn(vb.z, eb.z, Mb);
+                Ma = __fmaf_rn(va.w, ea.w, Ma); Mb = __fmaf_rn(vb.w, eb.w, Mb);
+            }
+            const float bna = resident ? bsm[ka] : __ldg(p.bn + ka), bnb = resident ? bsm[kb] : __ldg(p.bn + kb);
+            da = __fsub_rn(__fadd_rn(Aa, bna), __fmul_rn(2.0f, Ma));
+            db = __fsub_rn(__fadd_rn(Ab, bnb), __fmul_rn(2.0f, Mb));
+        };
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int zs = it & 1, par = it & 1;
             volatile int *fq = fq_all + par * 136;                 // [0] queue count, [1..128] queued rows, [135] pair count
+            int2 *prk = prk_all + par * PCAP;
+            float *pdist = pdist_all + par * PCAP;
             unsigned char *ztile = sm + OFF_Z + zs * ZSTAGE;
-            unsigned char *zrow = ztile + row * 128;
             ptx::mbar_wait_sleep(bar(Z_FULL + zs), (it >> 1) & 1, 200);
-            ptx::mbar_wait_sleep(bar(C_FULL + par), (uint32_t)((it >> 1) & 1), 200);
+            ptx::mbar_wait_sleep(bar(C_FULL + par), (uint32_t)((it >> 1) & 1), 32);
             if (ft == 0) VQ2_TL(it, 20);
             const int4 g0 = *reinterpret_cast<const int4 *>(cand + (par * 256 + row) * 4);
             const int4 g1 = *reinterpret_cast<const int4 *>(cand + (par * 256 + 128 + row) * 4);
@@ -489,13 +498,18 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             bool queued = n0 < 0 || n1 < 0;
             if (!queued && ncand == 1) {
                 // the only grid point: it holds the window's only code, provably the canonical argmin
-                if (n0 == 1) for_grid(g0, 0, [&](int k) { bk = k; });
-                else for_grid(g1, 1, [&](int k) { bk = k; });
+                const int4 g = n0 == 1 ? g0 : g1;
+                const int qi = __ffs(((int)g.z >> 8) & 3) - 1, ci = __ffs((int)g.z & 0xff) - 1;
+                const int bi = __ffs((int)((unsigned)g.y >> 16)) - 1, ri = __ffs((int)g.y & 0xffff) - 1;
+                bk = ((qi * 8 + ci) * 2 + (bi >> 3)) * CN + (n0 == 1 ? 0 : 128) + (bi & 7) * 16 + ri;
                 if (bk >= p.K) { bk = -1; queued = true; }
             } else if (!queued) {
                 // a few grid points: their (row, code) pairs join the tile's work list, re-scored densely below
                 pbase = atomicAdd(const_cast<int *>(&fq[135]), ncand);
-                if (pbase + ncand > PCAP) { queued = true; pbase = -1; }
+                if (pbase + ncand > PCAP) {
+                    for (int w = pbase; w < PCAP; ++w) prk[w] = make_int2(0, -1);       // (stale pairs of an earlier tile)
+                    queued = true; pbase = -1;
+                }
                 else {
                     int w = pbase;
                     auto push = [&](int k) { prk[w++] = make_int2(row, k < p.K ? k : -1); };
@@ -511,9 +525,14 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             if (ft == 0) VQ2_TL(it, 21);
             {
                 const int np = min((int)fq[135], PCAP);
-                for (int pi = ft; pi < np; pi += 128) {
-                    const int2 rk = prk[pi];
-                    if (rk.y >= 0) pdist[pi] = exact_dist(ztile + rk.x * 128, rk.x & 7, rk.y);
+                for (int pi = ft; pi < np; pi += 256) {        // two independent chains per thread: the chain latency, not the issue rate, bounds this phase
+                    const int2 ra = prk[pi];
+                    const int pj = pi + 128 < np ? pi + 128 : pi;
+                    const int2 rb2 = prk[pj];
+                    float da, db;
+                    exact_dist2(ztile + ra.x * 128, ra.x & 7, ra.y < 0 ? 0 : ra.y, ztile + rb2.x * 128, rb2.x & 7, rb2.y < 0 ? 0 : rb2.y, da, db);
+                    pdist[pi] = da;
+                    pdist[pj] = db;
                 }
             }
             if (ft == 0) VQ2_TL(it, 22);
@@ -556,47 +575,51 @@ vq2_kernel(const __grid_constant__ CUtensorMap tmz, const __grid_constant__ CUte
             if (ft == 0) { fq[0] = 0; fq[135] = 0; }      // this parity's counters are next used two tiles (>= two barriers) later
             if (bk < 0) bk = 0;
 
-            // ---- gather e_idx, straight-through z_q (in place over the z tile), SSE, histogram, idx ----
+            // ---- idx, histogram ----
             const long long grow = tile * TM + row;
-            const bool live = grow < p.N;
-            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;     // this row's sum of (e - z)^2: 4 fp32 partials, one double add per row
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                float o[8];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int c16 = 2 * c8 + u;                  // 16-byte piece of the 256-byte fp32 row
-                    const float4 zv = *reinterpret_cast<const float4 *>(zrow + (c16 >> 3) * ZATOM + (((c16 & 7) ^ rsw) << 4));
-                    float4 e4;
-                    if (resident) e4 = *reinterpret_cast<const float4 *>(code_ptr_smem(bk) + (c16 >> 3) * EATOM + (((c16 & 7) ^ (bk & 7)) << 4));
-                    else e4 = __ldg(reinterpret_cast<const float4 *>(p.E + (size_t)bk * DD) + c16);
-                    float4 df;
-                    df.x = __fsub_rn(e4.x, zv.x); df.y = __fsub_rn(e4.y, zv.y); df.z = __fsub_rn(e4.z, zv.z); df.w = __fsub_rn(e4.w, zv.w);
-                    o[4 * u + 0] = __fadd_rn(zv.x, df.x); o[4 * u + 1] = __fadd_rn(zv.y, df.y);     // quantizer.py:67
-                    o[4 * u + 2] = __fadd_rn(zv.z, df.z); o[4 * u + 3] = __fadd_rn(zv.w, df.w);
-                    rs0 = fmaf(df.x, df.x, rs0); rs1 = fmaf(df.y, df.y, rs1); rs2 = fmaf(df.z, df.z, rs2); rs3 = fmaf(df.w, df.w, rs3);
-                    if (!p.zq_bf16)
-                        *reinterpret_cast<float4 *>(zrow + (c16 >> 3) * ZATOM + (((c16 & 7) ^ rsw) << 4)) =
-                            make_float4(o[4 * u + 0], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-                }
-                if (p.zq_bf16) {
-                    // bf16 rows (128 B) over the first atom: piece c8 holds channels 8 c8 .. 8 c8 + 7.  It overwrites fp32 piece
-                    // c8 of atom 0 (channels 4 c8 ..), which this thread has already consumed (pieces are read in order 2 c8, 2 c8 + 1
-                    // >= c8).
-                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
-                    *reinterpret_cast<uint4 *>(zrow + ((c8 ^ rsw) << 4)) =
-                        make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
-                                   *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
-                }
-            }
-            if (live) {
-                sse += (double)((rs0 + rs1) + (rs2 + rs3));
+            if (grow < p.N) {
                 p.idx[grow] = bk;
                 if (smem_hist) atomicAdd(&hist_s[bk], 1);
                 else atomicAdd(&p.hist[bk], 1);
             }
-            ptx::fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
+            // ---- gather e_idx, straight-through z_q, SSE: one row per warp step, the lanes across its 64 columns (two
+            // each): two-wavefront shared-memory reads of the z row and of the code row, one coalesced 256- / 128-byte
+            // store of z_q.  (Thread-per-row with an in-place z_q tile + TMA store took 3700 + 1400 cycles of the tile's
+            // dependent chain, profiles/r02_vq2_timeline_k512_before.txt.) ----
+            {
+                const int wr0 = (warp - 12) * 32;
+                const int c16 = lane >> 1;
+                const uint32_t zc = (uint32_t)(c16 & 7);
+                const unsigned char *zb0 = ztile + wr0 * 128 + (c16 >> 3) * ZATOM + (lane & 1) * 8;
+                const uint32_t eoff = (uint32_t)((c16 >> 3) * EATOM + (lane & 1) * 8);
+                const long long g0r = tile * TM + wr0;
+                const bool full = g0r + 32 <= p.N;                  // every row of this warp is live (all tiles but the last)
+                float2 *zqf = reinterpret_cast<float2 *>(p.zq) + g0r * 32 + lane;
+                __nv_bfloat162 *zqh = reinterpret_cast<__nv_bfloat162 *>(p.zq) + g0r * 32 + lane;
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                for (int rb = 0; rb < 32; rb += 8) {
+                    float2 zv[8], ev[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = __shfl_sync(0xffffffffu, bk, rb + j);
+                        zv[j] = *reinterpret_cast<const float2 *>(zb0 + (rb + j) * 128 + ((zc ^ (uint32_t)j) << 4));      // (wr0 + rb + j) & 7 == j
+                        if (resident) ev[j] = *reinterpret_cast<const float2 *>(code_ptr_smem(k) + eoff + ((zc ^ (uint32_t)(k & 7)) << 4));
+                        else ev[j] = __ldg(reinterpret_cast<const float2 *>(p.E + (size_t)k * DD) + lane);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dx = __fsub_rn(ev[j].x, zv[j].x), dy = __fsub_rn(ev[j].y, zv[j].y);
+                        const float ox = __fadd_rn(zv[j].x, dx), oy = __fadd_rn(zv[j].y, dy);                    // quantizer.py:67
+                        if (full || g0r + rb + j < p.N) {
+                            acc0 = fmaf(dx, dx, acc0); acc1 = fmaf(dy, dy, acc1);
+                            if (ZQBF) zqh[(rb + j) * 32] = __floats2bfloat162_rn(ox, oy);
+                            else zqf[(rb + j) * 32] = make_float2(ox, oy);
+                        }
+                    }
+                }
+                sse += (double)(acc0 + acc1);       // this lane's 2 columns x 32 rows: fp32 partial, one double add per tile
+            }
             __syncwarp();
             if (ft == 0) VQ2_TL(it, 24);
             if (ft == 96) VQ2_TL(it, 25);
@@ -647,13 +670,10 @@ int launch_vq2(const float *z, const float *E, long long N, int K, int D, long l
     unsigned *scal = reinterpret_cast<unsigned *>(w + align256((size_t)Kpad * 4));
     double *partials = reinterpret_cast<double *>(w + align256((size_t)Kpad * 4) + 256);
 
-    CUtensorMap tmz, tme, tmq;
+    CUtensorMap tmz, tme;
     int rc = vqb_encode_tmap_2d(&tmz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, z, DD, (uint64_t)N, DD * 4, 32, TM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = vqb_encode_tmap_2d(&tme, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, E, DD, (uint64_t)K, DD * 4, 32, CN, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = zq_bf16 ? vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, zq, DD, (uint64_t)N, DD * 2, 64, TM, CU_TENSOR_MAP_SWIZZLE_128B)
-                 : vqb_encode_tmap_2d(&tmq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, zq, DD, (uint64_t)N, DD * 4, 32, TM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
 
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (size_t)K, s);
@@ -667,10 +687,12 @@ int launch_vq2(const float *z, const float *E, long long N, int K, int D, long l
     }
     static bool attr_set = false;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(vq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(vq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
-        if (e != cudaSuccess) return (int)e;
+        const void *kernels[4] = {(const void *)vq2_kernel<true, false>, (const void *)vq2_kernel<true, true>,
+                                  (const void *)vq2_kernel<false, false>, (const void *)vq2_kernel<false, true>};
+        for (const void *kf : kernels) {
+            e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+            if (e != cudaSuccess) return (int)e;
+        }
         attr_set = true;
     }
     int dev = 0, sms = 148;
@@ -683,10 +705,15 @@ int launch_vq2(const float *z, const float *E, long long N, int K, int D, long l
     p.E = E; p.bn = bn; p.scal = reinterpret_cast<const float *>(scal);
     p.N = N; p.K = K; p.nchunks = nchunks;
     p.nbits = 0;
-    p.idx = idx; p.partials = partials; p.hist = hist; p.zq_bf16 = zq_bf16;
+    p.idx = idx; p.partials = partials; p.hist = hist; p.zq_bf16 = zq_bf16; p.zq = zq;
     p.pending = reinterpret_cast<unsigned *>(w + vq_ws_marker_offset(K));
-    if (cudaError_t le = nchunks <= 2 ? vqb_launch(vq2_kernel<true>, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p)
-                                      : vqb_launch(vq2_kernel<false>, dim3((unsigned)grid), dim3(NT2), (size_t)SMEM_ALLOC, s, tmz, tme, tmq, p))
+    const dim3 gd((unsigned)grid), bd(NT2);
+    cudaError_t le;
+    if (nchunks <= 2) le = zq_bf16 ? vqb_launch(vq2_kernel<true, true>, gd, bd, (size_t)SMEM_ALLOC, s, tmz, tme, p)
+                                   : vqb_launch(vq2_kernel<true, false>, gd, bd, (size_t)SMEM_ALLOC, s, tmz, tme, p);
+    else le = zq_bf16 ? vqb_launch(vq2_kernel<false, true>, gd, bd, (size_t)SMEM_ALLOC, s, tmz, tme, p)
+                      : vqb_launch(vq2_kernel<false, false>, gd, bd, (size_t)SMEM_ALLOC, s, tmz, tme, p);
+    if (le != cudaSuccess)
         return (int)le;
     if (!defer) vq_tc_sum(partials, grid, sse, s);
     VQB_COUNT_LAUNCH(defer ? nlaunch - 1 : nlaunch);
