@@ -39,6 +39,25 @@ void convt_out_scatter_column(int n, int *co, int *ky, int *kx);
 int launch_convt_out_scatter(const void *in, const void *packed, int packed_rows, int w_row0, const float *bias, float *out, int B, int H,
                              int W, cudaStream_t s);
 
+#if VQB_DIAG
+// in-kernel timeline of CTA 0 (SM cycle counter), tools/diag/hconv_timeline.py; diagnostic builds only
+__device__ unsigned long long g_hconv_tl[32 * 16];
+extern "C" int vqb_debug_read_hconv_timeline(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 32 * 16) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_hconv_tl, sizeof(unsigned long long) * n));
+}
+#define HC_TL(it_, ev_)                                                                       \
+    do {                                                                                      \
+        if (blockIdx.x == 0 && (it_) >= 0 && (it_) < 32) {                                    \
+            unsigned long long t_;                                                            \
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_));                                \
+            g_hconv_tl[(it_) * 16 + (ev_)] = t_;                                              \
+        }                                                                                     \
+    } while (0)
+#else
+#define HC_TL(it_, ev_) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int HC_THREADS = 384;
@@ -145,7 +164,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             gx0 = tx * p.TW; gy0 = ty * p.BH; n0 = (int)t * p.BN;
         };
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+        int hit = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++hit) {
             int gx0, gy0, n0;
             tile_origin(tile, gx0, gy0, n0);
             // pull the halo tiles of the tile after next into L2 now: with <= 3 halo buffers the shared-memory load of a
@@ -159,6 +179,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             for (int k = 0; k < p.nchunks; ++k) {
                 ptx::mbar_wait_sleep(hempty((int)hb), hpar ^ 1, 100);
                 if (leader) {
+                    if (k < 2) HC_TL(hit, k);
                     ptx::mbar_expect_tx(hfull((int)hb), (uint32_t)p.halo_bytes);
                     tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), p.chunk_c0[k], gx0 - p.halo, n0,
                                 p.chunk_p[k], gy0 - p.halo);
@@ -188,14 +209,17 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 for (int i = 0; i < p.nsteps[ps]; ++stage) i = load_group(steps_s + ps * HC_MAX_STEPS, i, p.nsteps[ps], stage);
         } else {
             uint32_t ws = 0, wpar = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += G) {
+            int wit = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++wit) {
                 const int ps = (int)(tile % p.npass);
                 const int ns = p.nsteps[ps];
                 for (int i = 0; i < ns;) {
                     ptx::mbar_wait_sleep(wempty((int)ws), wpar ^ 1, 64);
+                    if (leader && i == 0) HC_TL(wit, 2);
                     i = load_group(steps_s + ps * HC_MAX_STEPS, i, ns, ws);
                     if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
                 }
+                if (leader) HC_TL(wit, 3);
             }
         }
     } else if (warp == 1) {
@@ -214,13 +238,18 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             const int acc = it & 1;
             const uint4 *sp = steps_s + ps * HC_MAX_STEPS;
             uint4 st = sp[0];
+            if (leader) HC_TL(it, 4);
             ptx::mbar_wait(tempty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+            if (leader) HC_TL(it, 5);
             const uint32_t dbase = tmem_base + (uint32_t)(acc * 256);
             if (resident) ws = ps == 0 ? 0u : (uint32_t)p.res_groups0;          // stage = group index over both passes
             for (int i = 0; i < ns; ++i) {
                 const uint4 nx = sp[i + 1];                                       // (one entry of slack behind the table)
                 const uint32_t fl = st.w;
-                if (fl & ST_NEWCHUNK) ptx::mbar_wait(hfull((int)hb), hpar);
+                if (fl & ST_NEWCHUNK) {
+                    ptx::mbar_wait(hfull((int)hb), hpar);
+                    if (leader && i == 0) HC_TL(it, 6);
+                }
                 if (fl & ST_GSTART) {
                     if (!resident) ptx::mbar_wait(wfull((int)ws), wpar);
                     else if (it < 2) ptx::mbar_wait(wfull((int)ws), 0);          // each pass first occurs at it <= 1
@@ -255,7 +284,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 }
                 st = nx;
             }
-            if (leader) ptx::tc_commit(tfull(acc));
+            if (leader) { HC_TL(it, 7); ptx::tc_commit(tfull(acc)); }
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -278,6 +307,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             const int acc = it & 1;
             ptx::mbar_wait_sleep(tfull(acc), (uint32_t)((it >> 1) & 1), 200);     // (parked warps must not poll: they outrank the MMA warp)
             ptx::tc_fence_after();
+            if (tid == 128) HC_TL(it, 8);
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + em * p.NCOL);
             if (p.epi_mode == EPI_SHUFFLE_NCHW) {
                 // decoder.py:34-35: column (py*2+px)*Cout+co of input pixel (gy,gx) is output pixel (2gy+py, 2gx+px),
@@ -350,6 +380,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             }
             ptx::tc_fence_before();
             __syncwarp();
+            if (tid == 128) HC_TL(it, 9);
+            if (tid == 352) HC_TL(it, 10);
             if (lane == 0) ptx::mbar_arrive(tempty(acc));
         }
     }

@@ -14,6 +14,12 @@ def _require_cuda(t, what):
         raise RuntimeError(
             f"vqvae_b200: {what} must be a CUDA tensor -- this implementation is sm_100a-only "
             "and has no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device's stream (header: "the caller selects the device"); a tensor that lives
+        # elsewhere would be read through a peer mapping at best and fault at worst
+        raise RuntimeError(
+            f"vqvae_b200: {what} is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "wrap the call in `with torch.cuda.device(tensor.device):`")
 
 
 def _stream():
