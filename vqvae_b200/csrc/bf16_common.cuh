@@ -40,6 +40,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
                  :: "memory");
 }
 
+// one 32-byte (full-sector) store per thread: sm_100 has 256-bit global stores (STG.E.ENL2.256)
+__device__ __forceinline__ void st_global_256(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::
+                     "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);

@@ -65,6 +65,21 @@ static inline cudaError_t vqb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.numAttrs = vqb_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+// same, as thread-block clusters of `cluster` CTAs along x (the grid must be a multiple of it)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vqb_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                             unsigned cluster, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = vqb_pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 #endif
 
 static inline int vqb_cuda_status(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }

@@ -93,12 +93,26 @@ struct HParams {
     int S, wst_bytes, resident, nhb, halo_bytes, halo_stride;     // S ring stages of wst_bytes (= largest step group)
     int epi_mode, cg, sy, sx, OH, OW, Cout, relu, out_f32, bias_mod;
     int res_groups0;                // resident mode: number of step groups (= ring stages) of pass 0
+    int cluster;                    // 2: CTA pairs share the weight stream (each loads every other step, multicast to both)
     HStep steps[2][HC_MAX_STEPS];
 };
 
 __device__ __forceinline__ void prefetch_l2_5d(const CUtensorMap *m, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::
                      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 template <int MT>
@@ -126,9 +140,14 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid < p.S) { ptx::mbar_init(wfull(tid), 1); ptx::mbar_init(wempty(tid), 1); }
-    if (tid >= 64 && tid < 64 + p.nhb) { ptx::mbar_init(hfull(tid - 64), 1); ptx::mbar_init(hempty(tid - 64), 1); }
-    if (tid >= 96 && tid < 98) { ptx::mbar_init(tfull(tid - 96), 1); ptx::mbar_init(tempty(tid - 96), 8); }
+    const bool paired = p.cluster == 2;                  // CTA pair sharing one weight stream (non-resident layers)
+    uint32_t crank = 0;
+    if (paired) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    // MT = 2: two MMA issuer warps (one per M half), each commits its own MMAs to every barrier the tensor pipe signals
+    constexpr uint32_t NISS = MT == 2 ? 2u : 1u;
+    if (tid < p.S) { ptx::mbar_init(wfull(tid), 1); ptx::mbar_init(wempty(tid), (paired ? 2u : 1u) * NISS); }
+    if (tid >= 64 && tid < 64 + p.nhb) { ptx::mbar_init(hfull(tid - 64), 1); ptx::mbar_init(hempty(tid - 64), NISS); }
+    if (tid >= 96 && tid < 98) { ptx::mbar_init(tfull(tid - 96), NISS); ptx::mbar_init(tempty(tid - 96), 8); }
     if (tid == 128) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w); ptx::prefetch_tmap(&tma_wh); }
     ptx::fence_mbar_init();
     for (int c = tid; c < p.NCOL; c += HC_THREADS) {
@@ -148,10 +167,15 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (paired) cluster_sync_all();                      // the peer's barriers exist before anything is multicast to them
     pdl_launch_dependents();
 
     const long long ntiles = p.ntiles;
     const int G = (int)gridDim.x;
+    // a CTA pair walks the weight stream in lockstep: both run as many iterations as the pair's first CTA has tiles; the
+    // second one may end with a "dry" iteration that only consumes (and helps to load) the weights
+    const long long pair_first = (long long)blockIdx.x - (long long)crank;
+    const long long niter = pair_first < ntiles ? (ntiles - pair_first + G - 1) / G : 0;
 
     if (warp == 0) {
         // ===================== halo producer =====================
@@ -195,9 +219,12 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             if (leader) ptx::mbar_expect_tx(wfull((int)stage), gbytes);
             for (;; ++i) {
                 const uint4 st = sp[i];
-                if (leader)
-                    ptx::tma_load_2d(sbase + ring_off + stage * (uint32_t)p.wst_bytes + (((st.z >> 8) & 0xfffu) << 4),
-                                     (st.w & ST_HALFBOX) ? &tma_wh : &tma_w, wfull((int)stage), 0, (int)((st.w >> 8) & 0xffffu));
+                if (leader) {
+                    const uint32_t dst = sbase + ring_off + stage * (uint32_t)p.wst_bytes + (((st.z >> 8) & 0xfffu) << 4);
+                    const CUtensorMap *wm = (st.w & ST_HALFBOX) ? &tma_wh : &tma_w;
+                    if (!paired) ptx::tma_load_2d(dst, wm, wfull((int)stage), 0, (int)((st.w >> 8) & 0xffffu));
+                    else if (((uint32_t)i & 1u) == crank) tma_load_2d_mc(dst, wm, wfull((int)stage), 0, (int)((st.w >> 8) & 0xffffu), (uint16_t)3);
+                }
                 if (st.w & ST_GEND) break;
             }
             (void)ns;
@@ -210,8 +237,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         } else {
             uint32_t ws = 0, wpar = 0;
             int wit = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++wit) {
-                const int ps = (int)(tile % p.npass);
+            for (long long k = 0, tile = blockIdx.x; k < niter; ++k, tile += G, ++wit) {
+                const int ps = (int)((tile < ntiles ? tile : pair_first + k * G) % p.npass);      // (a dry iteration follows the pair's first CTA)
                 const int ns = p.nsteps[ps];
                 for (int i = 0; i < ns;) {
                     ptx::mbar_wait_sleep(wempty((int)ws), wpar ^ 1, 64);
@@ -222,8 +249,14 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 if (leader) HC_TL(wit, 3);
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || (MT == 2 && warp == 2)) {
+        // ===================== MMA issuer(s) =====================
+        // The issue loop is ~16 dependent scalar instructions per MMA (descriptor arithmetic, register -> uniform-register
+        // moves, flag branches): one warp sustains an M128 N128 K16 MMA per ~96 cycles against the 64 the tensor pipe needs
+        // (r02_hconv_timeline_before.txt; tools/ubench/mma_rate2.cu shows that neither the halo-tile descriptors, nor
+        // concurrent tcgen05.ld, nor shared-memory stores slow the pipe itself).  With 256-pixel tiles the two M halves have
+        // separate accumulators, so warp 1 issues half 0 and warp 2 (free after the TMEM allocation) half 1.
+        const uint32_t mh = MT == 2 ? (uint32_t)(warp - 1) : 0u;
         const bool leader = ptx::elect_one();
         const uint32_t a_hi = ptx::desc_hi_sw128((uint32_t)(p.WP * 128)), b_hi = ptx::desc_hi_sw128(1024);
         const uint32_t ring16 = (sbase + ring_off) >> 4, wst16 = (uint32_t)p.wst_bytes >> 4;
@@ -232,15 +265,30 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         const bool resident = p.resident != 0;
         uint32_t hb = 0, hpar = 0, ws = 0, wpar = 0;
         int it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+        for (long long k = 0, tile = blockIdx.x; k < (paired ? niter : (ntiles - blockIdx.x + G - 1) / G); ++k, tile += G, ++it) {
+            if (tile >= ntiles) {
+                // dry iteration of a CTA pair: take part in the weight ring's hand-shake, nothing else
+                const int psd = (int)((pair_first + k * G) % p.npass);
+                const uint4 *spd = steps_s + psd * HC_MAX_STEPS;
+                for (int i = 0; i < p.nsteps[psd]; ++i) {
+                    const uint32_t fl = spd[i].w;
+                    if (fl & ST_GSTART) ptx::mbar_wait(wfull((int)ws), wpar);
+                    if (fl & ST_GEND) {
+                        if (leader) tc_commit_mc(wempty((int)ws), (uint16_t)3);
+                        if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             const int ps = (int)(tile % p.npass);
             const int ns = p.nsteps[ps];
             const int acc = it & 1;
             const uint4 *sp = steps_s + ps * HC_MAX_STEPS;
             uint4 st = sp[0];
-            if (leader) HC_TL(it, 4);
+            if (leader && mh == 0) HC_TL(it, 4);
             ptx::mbar_wait(tempty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
-            if (leader) HC_TL(it, 5);
+            if (leader && mh == 0) HC_TL(it, 5);
             const uint32_t dbase = tmem_base + (uint32_t)(acc * 256);
             if (resident) ws = ps == 0 ? 0u : (uint32_t)p.res_groups0;          // stage = group index over both passes
             for (int i = 0; i < ns; ++i) {
@@ -248,16 +296,16 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 const uint32_t fl = st.w;
                 if (fl & ST_NEWCHUNK) {
                     ptx::mbar_wait(hfull((int)hb), hpar);
-                    if (leader && i == 0) HC_TL(it, 6);
+                    if (leader && i == 0 && mh == 0) HC_TL(it, 6);
                 }
                 if (fl & ST_GSTART) {
                     if (!resident) ptx::mbar_wait(wfull((int)ws), wpar);
                     else if (it < 2) ptx::mbar_wait(wfull((int)ws), 0);          // each pass first occurs at it <= 1
                 }
                 ptx::tc_fence_after();
-                const uint32_t a_lo = halo16 + hb * hstride16 + st.x;
+                const uint32_t a_lo = halo16 + hb * hstride16 + st.x + mh * 64u;
                 const uint32_t b_lo = ring16 + ws * wst16 + ((st.z >> 8) & 0xfffu);
-                const uint32_t d0 = dbase + (st.z & 0xffu);
+                const uint32_t d0 = dbase + (st.z & 0xffu) + mh * ncol;
                 const uint32_t idesc = st.y;
                 const uint32_t accf = (fl & ST_FIRST) ? 0u : 1u;
                 if (leader) {
@@ -265,16 +313,10 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                     mma_bf16_w(d0, a_lo + 2u, a_hi, b_lo + 2u, b_hi, idesc, 1u);
                     mma_bf16_w(d0, a_lo + 4u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
                     mma_bf16_w(d0, a_lo + 6u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
-                    if (MT == 2) {
-                        mma_bf16_w(d0 + ncol, a_lo + 64u, a_hi, b_lo, b_hi, idesc, accf);
-                        mma_bf16_w(d0 + ncol, a_lo + 66u, a_hi, b_lo + 2u, b_hi, idesc, 1u);
-                        mma_bf16_w(d0 + ncol, a_lo + 68u, a_hi, b_lo + 4u, b_hi, idesc, 1u);
-                        mma_bf16_w(d0 + ncol, a_lo + 70u, a_hi, b_lo + 6u, b_hi, idesc, 1u);
-                    }
                 }
                 if (fl & ST_GEND) {
                     if (!resident) {
-                        if (leader) ptx::tc_commit(wempty((int)ws));
+                        if (leader) { if (paired) tc_commit_mc(wempty((int)ws), (uint16_t)3); else ptx::tc_commit(wempty((int)ws)); }
                         if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
                     } else ++ws;
                 }
@@ -284,7 +326,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 }
                 st = nx;
             }
-            if (leader) { HC_TL(it, 7); ptx::tc_commit(tfull(acc)); }
+            if (leader) { if (mh == 0) HC_TL(it, 7); ptx::tc_commit(tfull(acc)); }
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -335,19 +377,11 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                     if (!valid) return;
                     const int j = c0 / p.cg, cc = c0 - j * p.cg;
                     const long long off = (prow + j) * p.Cout + cc;
+                    // 32-byte stores: each thread writes whole sectors of its pixel's channel run (16-byte stores left half-written
+                    // sectors behind and cost twice the store instructions: the epilogue, not the MMAs, bounded the transposed
+                    // convolutions -- profiles/r02_hconv_timeline_before.txt)
                     if (p.out_f32) {
-                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (i < nc) {
-                                const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + i);
-                                float4 o = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
-                                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                                dst[i >> 2] = o;
-                            }
-                        }
-                    } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
+                        float *dst = reinterpret_cast<float *>(p.out) + off;
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
                             if (i < nc) {
@@ -357,7 +391,23 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                                     o[u] = v[i + u] + bias_s[c0 + i + u];
                                     if (p.relu) o[u] = fmaxf(o[u], 0.f);
                                 }
-                                dst[i >> 3] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                                st_global_256(dst + i, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                                              __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + off;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 16) {
+                            if (i < nc) {
+                                float o[16];
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) {
+                                    o[u] = v[i + u] + bias_s[c0 + i + u];
+                                    if (p.relu) o[u] = fmaxf(o[u], 0.f);
+                                }
+                                st_global_256(dst + i, pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]),
+                                              pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
                             }
                         }
                     }
@@ -388,6 +438,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+    if (paired) cluster_sync_all();                      // neither CTA leaves while the other may still signal its barriers
 }
 
 // ------------------------------------------------------------------------------------------------ host side: plans
@@ -612,10 +663,11 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
         return launch_convt_out_scatter(in, packed, (int)pl->rows.size(), pl->scatter_row0, bias, reinterpret_cast<float *>(out), B, H, W, s);
 
     HParams q;
-    memset(&q, 0, sizeof(q));
-    q.bias = bias; q.out = out;
     // the GEMM's pixel grid: the input grid, or the space-to-depth grid of a stride-2 conv
     const int GH = pl->s2d ? H / 2 : H, GW = pl->s2d ? W / 2 : W;
+    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4) + 16 + 256 * 4 + 2 * HC_MAX_STEPS * 16 + 16 + 1024;
+    memset(&q, 0, sizeof(q));
+    q.bias = bias; q.out = out;
     q.B = B; q.H = GH; q.W = GW;
     q.MT = (GW > 8 && 2 * pl->NCOL <= 256) ? 2 : 1;
     q.TW = 8 * q.MT;
@@ -668,9 +720,15 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
     q.halo_stride = (q.halo_bytes + 1023) & ~1023;
     q.wst_bytes = (max_group_bytes + 1023) & ~1023;
     q.nhb = HC_MAX_HB;
-    constexpr int MISC = 8 * (2 * HC_MAX_STAGES + 2 * HC_MAX_HB + 4) + 16 + 256 * 4 + 2 * HC_MAX_STEPS * 16 + 16 + 1024;
     int S = (227 * 1024 - q.nhb * q.halo_stride - MISC) / q.wst_bytes;
-    if (S < 2) { q.nhb = 2; S = (227 * 1024 - q.nhb * q.halo_stride - MISC) / q.wst_bytes; }
+    {
+        // The weight ring is latency bound (profiles/r02_hconv_timeline_before.txt: 3 x 32 KB in flight deliver ~21 B per
+        // cycle against the 32 B per cycle a full-rate N = 128 MMA stream consumes), so shared memory is worth more as a
+        // ring stage than as a third halo buffer when a tile has at most two chunks: the next tile's first chunk then loads
+        // (from L2, prefetched two tiles ahead) behind the MMAs of this tile's last chunk.
+        const int S2 = (227 * 1024 - 2 * q.halo_stride - MISC) / q.wst_bytes;
+        if (S < 2 || (pl->nchunks <= 2 && S2 > S)) { q.nhb = 2; S = S2; }
+    }
     if (S > HC_MAX_STAGES) S = HC_MAX_STAGES;
     if (S < 2) return VQB_ERR_UNSUPPORTED;
     const int all_groups = ngroups[0] + ngroups[1];
@@ -718,9 +776,21 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
-    const cudaError_t le = q.MT == 2 ? vqb_launch(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)
-                                     : vqb_launch(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q);
+    int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
+    // Streamed weights can be shared by CTA pairs (clusters of 2): each CTA loads every other step and multicasts it to both,
+    // halving the L2 -> shared-memory requests per SM.  Parity-green, but it changes nothing (E3 133 vs 130 us, E2 139 vs 139,
+    // D1 80 vs 79): the weight stream was never the limit, the MMA issuer's own instruction stream was (see the issuer
+    // warps).  Off by default.
+    constexpr bool HC_PAIR_WEIGHTS = false;
+    q.cluster = (HC_PAIR_WEIGHTS && !q.resident && q.npass == 1 && grid >= 2) ? 2 : 1;
+    if (q.cluster == 2) grid &= ~1;
+    cudaError_t le;
+    if (q.cluster == 2)
+        le = q.MT == 2 ? vqb_launch_cluster(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, 2u, tin, tw, twh, q)
+                       : vqb_launch_cluster(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, 2u, tin, tw, twh, q);
+    else
+        le = q.MT == 2 ? vqb_launch(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)
+                       : vqb_launch(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q);
     if (le != cudaSuccess) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
