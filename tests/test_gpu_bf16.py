@@ -90,6 +90,47 @@ def test_bf16_conv_many_tiles_persistent_loop():
     _run_layer(rng, 4, 128, 64, 64, 64, 4, 2, True, True, False)          # 2 passes x 256 tiles
 
 
+def test_bf16_kernels_back_to_back_launches():
+    """40 launches of each persistent kernel enqueued without a host sync (programmatic dependent launch lets a launch start
+    while its predecessor drains): every launch must give the first launch's bits.  Written after a two-issuer variant of
+    the residual kernel passed all single-launch tests and faulted about once in thirty launches (r02_hconv_notes.txt)."""
+    from vqvae_b200 import ops, _lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, L = 48, 64
+    jobs = []
+
+    def conv(Cin, H, W, Cout, k, stride, transposed, out_f32=False, relu=True):
+        x = torch.randn((B, H, W, Cin), device="cuda", generator=g).to(torch.bfloat16)
+        wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+        w = torch.randn(wshape, device="cuda", generator=g) / np.sqrt(Cin * k * k)
+        b = torch.randn((Cout,), device="cuda", generator=g) * 0.1
+        kind = ops.conv_kind(k, stride, transposed, Cout)
+        pk = ops.pack_conv_weight_bf16(w, kind)
+        jobs.append(lambda: ops.conv2d_bf16(x, pk, b, B=B, Cin=Cin, H=H, W=W, Cout=Cout, kind=kind, relu=relu, out_f32=out_f32))
+
+    conv(64, 2 * L, 2 * L, 128, 4, 2, False)          # E2
+    conv(128, L, L, 128, 3, 1, False)                 # E3 (two MMA issuer warps, streamed weights)
+    conv(64, L, L, 128, 3, 1, True)                   # D1
+    conv(128, L, L, 64, 4, 2, True)                   # D2 (two passes)
+    conv(128, L, L, 64, 1, 1, False, True, False)     # pre-quant 1x1 (resident weights)
+    conv(64, 2 * L, 2 * L, 3, 4, 2, True, True, False)  # D3, scatter form
+    r = torch.randn((B, L, L, 128), device="cuda", generator=g).clamp_min(0).to(torch.bfloat16)
+    w1 = torch.randn((32, 128, 3, 3), device="cuda", generator=g) / np.sqrt(1152)
+    w2 = torch.randn((128, 32, 1, 1), device="cuda", generator=g) / np.sqrt(32)
+    p1, p2 = ops.pack_conv_weight_bf16(w1, _lib.CONV_K3), ops.pack_conv_weight_bf16(w2, _lib.RES_W2)
+    jobs.append(lambda: ops.residual_layer_bf16(r, p1, p2, B=B, H=L, W=L, C=128, Cmid=32, relu_out=True))
+    xi = torch.rand((B, 3, 4 * L, 4 * L), device="cuda", generator=g) * 2 - 1
+    wi = ops.pack_conv_weight(torch.randn((64, 3, 4, 4), device="cuda", generator=g) / 7, False)
+    bi = torch.zeros((64,), device="cuda")
+    jobs.append(lambda: ops.conv_in_bf16(xi, wi, bi, B=B, H=4 * L, W=4 * L, Cout=64))
+    for job in jobs:
+        outs = [job() for _ in range(40)]
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+        del outs
+
+
 @pytest.mark.parametrize("B,H,W,C,Cmid,relu_out", [(2, 16, 32, 128, 32, True), (1, 64, 64, 128, 32, True), (3, 8, 8, 128, 32, True),
                                                    (2, 20, 36, 128, 32, False), (5, 8, 8, 64, 16, True), (6, 64, 64, 128, 32, True)])
 def test_bf16_residual_layer_vs_oracle(B, H, W, C, Cmid, relu_out):

@@ -67,9 +67,9 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, W = p.W, OW = W / 2, OH = H / 2, R = p.R, NR = 2 * R + 2;
     if (tid == 0) {
-        for (int s = 0; s < NRAW; ++s) { ptx::mbar_init(rfull(s), 1); ptx::mbar_init(rempty(s), 8); }
+        for (int s = 0; s < NRAW; ++s) { ptx::mbar_init(rfull(s), 1); ptx::mbar_init(rempty(s), 4); }
         for (int s = 0; s < NA; ++s) {
-            ptx::mbar_init(afull(s), 8); ptx::mbar_init(aempty(s), 1);
+            ptx::mbar_init(afull(s), 4); ptx::mbar_init(aempty(s), 1);
             ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4);
         }
         for (int s = 0; s < NA; ++s) ptx::mbar_init(sfree(s), 1);
@@ -131,15 +131,21 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     } else if (warp >= 4 && warp < 12) {
         // ===================== im2col builders: thread = (pixel, kernel-row half) =====================
         const int bt = tid - 128;
-        const int row = bt & 127, hf = bt >> 7;
+        // Two groups of four warps build ALTERNATE tiles (thread = pixel, both kernel-row halves): a tile's build is one long
+        // dependent chain per thread (loads -> stores -> proxy fence -> arrive), so with all eight warps on the same tile the
+        // stage time was that chain's latency; two tiles in flight halve it.
+        const int row = bt & 127, grp = bt >> 7;
         const int r = row >> p.log2_ow, ox = row & (OW - 1);
-        int it = 0;
-        uint32_t rs = 0, rpar = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+        int it = grp;
+        for (long long tile = (long long)blockIdx.x + (long long)grp * G; tile < ntiles; tile += 2LL * G, it += 2) {
             const int s = it % NA;
+            const uint32_t rs = (uint32_t)(it % NRAW), rpar = (uint32_t)((it / NRAW) & 1);
             ptx::mbar_wait_sleep(rfull((int)rs), rpar, 32);
             ptx::mbar_wait_sleep(aempty(s), (uint32_t)(((it / NA) & 1) ^ 1), 32);
             const float *rawp = reinterpret_cast<const float *>(sm + raw_off + rs * raw_stride);
+            unsigned char *arow = sm + s * A_BYTES + row * 128;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
             float v[24];                                          // k_local = (trl*4 + s)*3 + c
 #pragma unroll
             for (int trl = 0; trl < 2; ++trl)
@@ -152,15 +158,14 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                     v[(trl * 4 + 2) * 3 + c] = mid.y;
                     v[(trl * 4 + 3) * 3 + c] = ox < OW - 1 ? b[2] : 0.f;
                 }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(rempty((int)rs));     // the staged rows may be overwritten
-            if (++rs == NRAW) { rs = 0; rpar ^= 1; }
-            unsigned char *arow = sm + s * A_BYTES + row * 128;
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 const int kq = hf * 24 + 4 * q, atom = kq >> 5, c16 = (kq & 31) >> 2;
                 *reinterpret_cast<float4 *>(arow + atom * 16384 + ((c16 ^ (row & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(rempty((int)rs));     // the staged rows may be overwritten
             ptx::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(afull(s));
