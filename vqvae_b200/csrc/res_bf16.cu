@@ -27,10 +27,30 @@
 
 int hconv_plan_rows(int kind, int Cin, int Cout);
 
+#if VQB_DIAG
+// in-kernel timeline of CTA 0 (SM cycle counter), tools/diag/res_timeline.py; diagnostic builds only
+__device__ unsigned long long g_res_tl[32 * 16];
+extern "C" int vqb_debug_read_res_timeline(unsigned long long *dst, int n) {
+    if (!dst || n < 1 || n > 32 * 16) return VQB_ERR_BAD_ARG;
+    return vqb_cuda_status(cudaMemcpyFromSymbol(dst, g_res_tl, sizeof(unsigned long long) * n));
+}
+#define RB_TL(it_, ev_)                                                                       \
+    do {                                                                                      \
+        if (blockIdx.x == 0 && (it_) >= 0 && (it_) < 32) {                                    \
+            unsigned long long t_;                                                            \
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_));                                \
+            g_res_tl[(it_) * 16 + (ev_)] = t_;                                                \
+        }                                                                                     \
+    } while (0)
+#else
+#define RB_TL(it_, ev_) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int RB_THREADS = 512;       // warps: 0 halo producer, 1 MMA issuer, 2 TMEM + weights, 3 skip producer, 4-11 epilogue 2, 12-15 epilogue 1
 constexpr int RB_NHB = 3;             // halo buffers, rotating over the (tile, chunk) sequence
+constexpr int RB_NISS = 2;            // GEMM1 issuer warps (warp 1: K steps 0-1 of every tap, warp 2: K steps 2-3; private accumulators)
 
 struct ResBfParams {
     int B, H, W, C, Cmid;
@@ -78,10 +98,11 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int b = 0; b < 3; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), 1); }
+        // two GEMM1 issuer warps: each commits its own MMAs to the barriers the tensor pipe signals
+        for (int b = 0; b < 3; ++b) { ptx::mbar_init(hfull(b), 1); ptx::mbar_init(hempty(b), RB_NISS); }
         ptx::mbar_init(wfull, 1);
         for (int s = 0; s < 2; ++s) {
-            ptx::mbar_init(d1full(s), 1); ptx::mbar_init(d1empty(s), 4);
+            ptx::mbar_init(d1full(s), RB_NISS); ptx::mbar_init(d1empty(s), 4);
             ptx::mbar_init(d2full(s), 1); ptx::mbar_init(d2empty(s), 8);
             ptx::mbar_init(sfull(s), 1); ptx::mbar_init(sfree(s), 1);
         }
@@ -100,6 +121,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
     const long long ntiles = p.ntiles;
     const int G = (int)gridDim.x;
     const uint32_t D2COL = 256;                 // D1: 2 stages x Cmid columns from 0; D2: 2 stages x C columns from 256
+    const uint32_t D1BCOL = 128;                // the second GEMM1 issuer's partial sums: 2 stages x Cmid columns from 128
 
     if (warp == 0) {
         // ===================== producer: halo tiles (GEMM1's A operand) and skip tiles (epilogue 2) =====================
@@ -128,6 +150,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             for (int c = 0; c < chunks; ++c) {
                 ptx::mbar_wait_sleep(hempty((int)hb), hpar ^ 1, 100);
                 if (leader) {
+                    if (c == 0) RB_TL(it, 0);
                     ptx::mbar_expect_tx(hfull((int)hb), (uint32_t)p.halo_bytes);
                     tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), c * 64, gx0 - 1, n0, 0, gy0 - 1);
                 }
@@ -149,6 +172,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             for (int c = 0; c < chunks; ++c) {
                 ptx::mbar_wait_sleep(sfree(c), (uint32_t)((it & 1) ^ 1), 100);           // the previous tile's store has read the buffer
                 if (leader) {
+                    if (c == 0) RB_TL(it, 1);
                     ptx::mbar_expect_tx(sfull(c), 16384u);
                     tma_load_5d(sbase + st_off + (uint32_t)c * 16384u, &tma_skip, sfull(c), c * 64, gx0, n0, 0, gy0);
                 }
@@ -161,6 +185,43 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             for (int i = 0; i < 9 * chunks; ++i)
                 ptx::tma_load_2d(sbase + w1_off + (uint32_t)i * w1_step, &tma_w1, wfull, 0, i * Cmid);
             ptx::tma_load_2d(sbase + w2_off, &tma_w2, wfull, 0, 0);
+        }
+        __syncwarp();
+        // ===================== second GEMM1 issuer: K steps 2-3 of every (chunk, tap) into its own accumulator =====================
+        // One warp issues an N = 32 MMA per ~39 cycles (its own scalar instruction stream; the pipe needs 16), and GEMM1's
+        // 36 x chunks MMAs made the issuer warp the busiest unit of the kernel -- all 4.05k cycles of a tile's period
+        // (profiles/r02_res_timeline_before.txt).  Both issuers walk the SAME sequence of halo-buffer uses and both release
+        // every one of them (count 2), so neither can get a parity ahead of the other (r02_hconv_notes.txt, section 5).
+        {
+            const bool leader = ptx::elect_one();
+            const uint32_t a_hi = ptx::desc_hi_sw128((uint32_t)(p.WP * 128)), k_hi = ptx::desc_hi_sw128(1024);
+            const uint32_t idesc1 = ptx::instr_desc(ptx::FMT_BF16, 128, (uint32_t)Cmid);
+            const uint32_t halo16 = sbase >> 4, hstride16 = (uint32_t)p.halo_stride >> 4;
+            const uint32_t w1_16 = (sbase + w1_off) >> 4, w1s16 = w1_step >> 4;
+            uint32_t hb = 0, hpar = 0;
+            ptx::mbar_wait(wfull, 0);
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+                ptx::mbar_wait(d1empty(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1));
+                const uint32_t d1 = tmem_base + D1BCOL + (uint32_t)((it & 1) * Cmid);
+                for (int c = 0; c < chunks; ++c) {
+                    ptx::mbar_wait(hfull((int)hb), hpar);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint32_t a_lo = halo16 + hb * hstride16 + p.a_off16[t];
+                        const uint32_t b_lo = w1_16 + (uint32_t)(c * 9 + t) * w1s16;
+#pragma unroll
+                        for (int kk = 2; kk < 4; ++kk)
+                            if (leader) mma_bf16_w(d1, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, k_hi, idesc1, (c == 0 && t == 0 && kk == 2) ? 0u : 1u);
+                    }
+                    if (leader) ptx::tc_commit(hempty((int)hb));
+                    __syncwarp();
+                    if (++hb == RB_NHB) { hb = 0; hpar ^= 1; }
+                }
+                if (leader) ptx::tc_commit(d1full(it & 1));
+                __syncwarp();
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -175,16 +236,17 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         auto gemm1_chunk = [&](int it, int c) {
             ptx::mbar_wait(hfull((int)hb), hpar);
             ptx::tc_fence_after();
+            if (leader) RB_TL(it, 2 + 2 * (c & 1));
             const uint32_t d1 = tmem_base + (uint32_t)((it & 1) * Cmid);
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const uint32_t a_lo = halo16 + hb * hstride16 + p.a_off16[t];
                 const uint32_t b_lo = w1_16 + (uint32_t)(c * 9 + t) * w1s16;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < 2; ++kk)          // (K steps 2-3: the second issuer, warp 2)
                     if (leader) mma_bf16_w(d1, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, k_hi, idesc1, (c == 0 && t == 0 && kk == 0) ? 0u : 1u);
             }
-            if (leader) ptx::tc_commit(hempty((int)hb));     // this halo buffer may take a later chunk
+            if (leader) { RB_TL(it, 3 + 2 * (c & 1)); ptx::tc_commit(hempty((int)hb)); }     // this halo buffer may take a later chunk
             __syncwarp();
             if (++hb == RB_NHB) { hb = 0; hpar ^= 1; }
         };
@@ -204,8 +266,10 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
                 gemm1_chunk(it + 1, 0);
             }
             ptx::mbar_wait(a2ready, (uint32_t)(it & 1));
+            if (leader) RB_TL(it, 6);
             ptx::mbar_wait(d2empty(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1));
             ptx::tc_fence_after();
+            if (leader) RB_TL(it, 7);
             for (int kk = 0; kk < Cmid / 16; ++kk)
                 if (leader) mma_bf16_w(tmem_base + D2COL + (uint32_t)((it & 1) * C), a2_16 + 2u * kk, k_hi, w2_16 + 2u * kk, k_hi, idesc2, kk > 0 ? 1u : 0u);
             if (leader) ptx::tc_commit(d2full(it & 1));
@@ -226,10 +290,14 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             ptx::mbar_wait_sleep(d1full(it & 1), (uint32_t)((it >> 1) & 1), 100);
             ptx::tc_fence_after();
+            if (tid == 384) RB_TL(it, 8);
             const uint32_t d1 = lane_t + (uint32_t)((it & 1) * Cmid);
             for (int c0 = 0; c0 < Cmid; c0 += 16) {
-                float v[16];
+                float v[16], w[16];
                 tmem_ld16(d1 + (uint32_t)c0, v);
+                tmem_ld16(d1 + D1BCOL + (uint32_t)c0, w);                    // + the second issuer's partial sums, fixed order
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += w[i];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint4 o = make_uint4(pack_bf16(fmaxf(v[h * 8 + 0], 0.f), fmaxf(v[h * 8 + 1], 0.f)),
@@ -243,6 +311,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             ptx::fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
             ptx::tc_fence_before();
             __syncwarp();
+            if (tid == 384) RB_TL(it, 9);
             if (lane == 0) { ptx::mbar_arrive(a2ready); ptx::mbar_arrive(d1empty(it & 1)); }
         }
     } else if (warp >= 4) {
@@ -262,8 +331,10 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
             unsigned char *srow = sm + st_off + chunk * 16384 + row * 128;
             ptx::mbar_wait_sleep(sfull(chunk), (uint32_t)(it & 1), 200);
+            if (tid == 128) RB_TL(it, 10);
             ptx::mbar_wait_sleep(d2full(it & 1), (uint32_t)((it >> 1) & 1), 200);
             ptx::tc_fence_after();
+            if (tid == 128) RB_TL(it, 11);
             const uint32_t d2 = lane_t + D2COL + (uint32_t)((it & 1) * C);
             for (int c0 = col0; c0 < col0 + cpg; c0 += 32) {
                 float v[32];
@@ -294,9 +365,11 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             if (chunks == 2) ptx::named_bar_sync(1 + g, 128);
             else ptx::named_bar_sync(1, 256);
             if (storer) {
+                if (tid == 128) RB_TL(it, 12);
                 tma_store_5d(&tma_out, sbase + st_off + (uint32_t)chunk * 16384u, chunk * 64, gx0, n0, 0, gy0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (tid == 128) RB_TL(it, 13);
                 ptx::mbar_arrive(sfree(chunk));
             }
         }
