@@ -60,7 +60,6 @@ struct ResBfParams {
     int chunks, halo_bytes, halo_stride;
     int relu_out;
     uint32_t a_off16[9];
-    const __nv_bfloat16 *r;      // the layer input again: epilogue 2 reads the skip connection straight from it (L2 hits)
 };
 
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
@@ -69,7 +68,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, uint32_t src,
 }
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
-res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
+res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_skip,
                 const __grid_constant__ CUtensorMap tma_w1, const __grid_constant__ CUtensorMap tma_w2,
                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ ResBfParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -110,7 +109,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
         ptx::mbar_init(a2ready, 4);
         ptx::fence_mbar_init();
     }
-    if (tid == 32) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_w1); }
+    if (tid == 32) { ptx::prefetch_tmap(&tma_in); ptx::prefetch_tmap(&tma_skip); ptx::prefetch_tmap(&tma_w1); }
     if (tid == 64) { ptx::prefetch_tmap(&tma_w2); ptx::prefetch_tmap(&tma_out); }
     if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 192, 512);
     ptx::tc_fence_before();
@@ -156,6 +155,27 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
                     tma_load_5d(sbase + hb * (uint32_t)p.halo_stride, &tma_in, hfull((int)hb), c * 64, gx0 - 1, n0, 0, gy0 - 1);
                 }
                 if (++hb == RB_NHB) { hb = 0; hpar ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== skip producer: the tile's own pixels into the staging buffers (epilogue 2 adds them) =====================
+        // A separate warp: behind the halo loads in one loop, the wait for the previous tile's store (sfree) kept the NEXT
+        // tile's halo request back until epilogue 2 had finished -- the halo then had less than one chunk time to arrive.
+        const bool leader = ptx::elect_one();
+        pdl_wait();
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+            long long t = tile;
+            const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
+            const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
+            const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
+            for (int c = 0; c < chunks; ++c) {
+                ptx::mbar_wait_sleep(sfree(c), (uint32_t)((it & 1) ^ 1), 100);           // the previous tile's store has read the buffer
+                if (leader) {
+                    if (c == 0) RB_TL(it, 1);
+                    ptx::mbar_expect_tx(sfull(c), 16384u);
+                    tma_load_5d(sbase + st_off + (uint32_t)c * 16384u, &tma_skip, sfull(c), c * 64, gx0, n0, 0, gy0);
+                }
             }
         }
     } else if (warp == 2) {
@@ -303,8 +323,6 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
         const int col0 = g * cpg;
         const int chunk = col0 >> 6;                      // staging buffer (64 channels) this group writes
         const bool storer = (chunks == 2) ? (q == 0 && lane == 0) : (g == 0 && q == 0 && lane == 0);
-        const int xx = row & 7, grp = row >> 3, bn = grp % p.BN, yy = grp / p.BN;      // this thread's pixel inside the tile
-        pdl_wait();                                       // the skip values are the previous layer's output
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
             long long t = tile;
@@ -312,37 +330,13 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
             unsigned char *srow = sm + st_off + chunk * 16384 + row * 128;
-            // The skip connection = this thread's own pixel of the layer input, read straight from global memory (an L2 hit:
-            // the halo tile holding it was loaded a moment ago) with 32-byte loads issued BEFORE the wait for GEMM2.  It used to
-            // arrive by TMA in the staging buffer the output leaves from, which chained store(t) -> skip load(t+1) -> epilogue
-            // (t+1) through that one buffer: 0.7k + 1.5k + 1.5k cycles = the whole 4k-cycle tile period
-            // (profiles/r02_res_timeline_before.txt).
-            uint32_t sk[32];
-            {
-                const int gx = gx0 + xx, gy = gy0 + yy, n = n0 + bn;
-                const bool valid = gx < p.W && gy < p.H && n < p.B;
-                const __nv_bfloat16 *sp = p.r + (((size_t)n * p.H + gy) * p.W + gx) * C + col0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) sk[8 * j + u] = 0u;
-                    if (valid && 16 * j < cpg)
-                        asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(sk[8 * j]), "=r"(sk[8 * j + 1]), "=r"(sk[8 * j + 2]), "=r"(sk[8 * j + 3]), "=r"(sk[8 * j + 4]),
-                                       "=r"(sk[8 * j + 5]), "=r"(sk[8 * j + 6]), "=r"(sk[8 * j + 7])
-                                     : "l"(sp + 16 * j) : "memory");
-                }
-            }
+            ptx::mbar_wait_sleep(sfull(chunk), (uint32_t)(it & 1), 200);
             if (tid == 128) RB_TL(it, 10);
             ptx::mbar_wait_sleep(d2full(it & 1), (uint32_t)((it >> 1) & 1), 200);
             ptx::tc_fence_after();
             if (tid == 128) RB_TL(it, 11);
-            ptx::mbar_wait(sfree(chunk), (uint32_t)((it & 1) ^ 1));          // the previous tile's store has read the staging buffer
             const uint32_t d2 = lane_t + D2COL + (uint32_t)((it & 1) * C);
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                if (cb * 32 >= cpg) break;
-                const int c0 = col0 + cb * 32;
+            for (int c0 = col0; c0 < col0 + cpg; c0 += 32) {
                 float v[32];
                 ptx::tmem_ld32(d2 + (uint32_t)c0, v);
                 ptx::tmem_ld_wait32(v);
@@ -350,11 +344,12 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in,
                 for (int i = 0; i < 4; ++i) {
                     const int piece = ((c0 & 63) >> 3) + i;                      // 16-byte piece of the 128-byte row
                     uint4 *ptr = reinterpret_cast<uint4 *>(srow + ((piece ^ (row & 7)) << 4));
+                    const uint4 s4 = *ptr;
+                    const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
                     uint32_t ow[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const uint32_t swd = sk[16 * cb + 4 * i + u];
-                        const __nv_bfloat162 sb = *reinterpret_cast<const __nv_bfloat162 *>(&swd);
+                        const __nv_bfloat162 sb = *reinterpret_cast<const __nv_bfloat162 *>(&sw[u]);
                         float o0 = v[8 * i + 2 * u] + __low2float(sb), o1 = v[8 * i + 2 * u + 1] + __high2float(sb);
                         if (p.relu_out) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
                         ow[u] = pack_bf16(o0, o1);
@@ -409,7 +404,6 @@ extern "C" int vqb_residual_layer_bf16(const void *r, const void *w1_packed, con
     ResBfParams q;
     memset(&q, 0, sizeof(q));
     q.B = B; q.H = H; q.W = W; q.C = C; q.Cmid = Cmid; q.relu_out = relu_out;
-    q.r = reinterpret_cast<const __nv_bfloat16 *>(r);
     q.chunks = C / 64;
     q.BH = rb_pow2_ceil(H) < 16 ? rb_pow2_ceil(H) : 16;
     q.BN = 16 / q.BH;
@@ -420,7 +414,7 @@ extern "C" int vqb_residual_layer_bf16(const void *r, const void *w1_packed, con
     q.halo_stride = (q.halo_bytes + 1023) & ~1023;
     for (int t = 0; t < 9; ++t) q.a_off16[t] = (uint32_t)(((t / 3) * q.BN * q.WP + (t % 3)) * 8);     // tap (r,s): dy+1 = r, dx+1 = s
 
-    CUtensorMap tin, tw1, tw2, tout;
+    CUtensorMap tin, tskip, tw1, tw2, tout;
     {
         typedef unsigned long long u64;
         const u64 dims[5] = {(u64)C, (u64)W, (u64)B, 1, (u64)H};
@@ -428,6 +422,8 @@ extern "C" int vqb_residual_layer_bf16(const void *r, const void *w1_packed, con
         const uint32_t box[5] = {64u, (uint32_t)q.WP, (uint32_t)q.BN, 1u, (uint32_t)(q.BH + 2)};
         const uint32_t tbox[5] = {64u, 8u, (uint32_t)q.BN, 1u, (uint32_t)q.BH};
         int rc = vqb_encode_tmap_nd(&tin, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, r, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = vqb_encode_tmap_nd(&tskip, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, r, 5, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
         rc = vqb_encode_tmap_nd(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, 5, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
@@ -451,7 +447,7 @@ extern "C" int vqb_residual_layer_bf16(const void *r, const void *w1_packed, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
-    if (cudaError_t le = vqb_launch(res_bf16_kernel, dim3((unsigned)grid), dim3(RB_THREADS), (size_t)smem, s, tin, tw1, tw2, tout, q)) return (int)le;
+    if (cudaError_t le = vqb_launch(res_bf16_kernel, dim3((unsigned)grid), dim3(RB_THREADS), (size_t)smem, s, tin, tskip, tw1, tw2, tout, q)) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
 }
