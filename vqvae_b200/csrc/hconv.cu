@@ -777,10 +777,11 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
-    // Streamed weights can be shared by CTA pairs (clusters of 2): each CTA loads every other step and multicasts it to both,
-    // halving the L2 -> shared-memory requests per SM.  Parity-green, but it changes nothing (E3 133 vs 130 us, E2 139 vs 139,
-    // D1 80 vs 79): the weight stream was never the limit, the MMA issuer's own instruction stream was (see the issuer
-    // warps).  Off by default.
+    // Streamed weights CAN be shared by CTA pairs (clusters of 2): each CTA loads every other step and multicasts it to both,
+    // halving the L2 -> shared-memory requests per SM; the ring's empty barriers take the commits of both CTAs
+    // (tcgen05.commit multicast), a pair's last CTA may end with a dry iteration.  Parity-green (all bf16 tests incl. the
+    // back-to-back stress), but within box-to-box noise both with one issuer (E3 133 vs 130 us) and with two (E3 117 vs 121,
+    // while the unpaired two-pass layer moved by the same 2-3 % on that box): the weight stream is not the limit.  Off.
     constexpr bool HC_PAIR_WEIGHTS = false;
     q.cluster = (HC_PAIR_WEIGHTS && !q.resident && q.npass == 1 && grid >= 2) ? 2 : 1;
     if (q.cluster == 2) grid &= ~1;
