@@ -115,7 +115,12 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int MT>
+// CTA pairs sharing the weight stream (see the launcher): compiled in only on request -- measured to make no difference
+#ifndef HC_PAIR_WEIGHTS
+#define HC_PAIR_WEIGHTS 0
+#endif
+
+template <int MT, bool RES>
 __global__ void __launch_bounds__(HC_THREADS, 1)
 hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
              const __grid_constant__ CUtensorMap tma_wh, const __grid_constant__ HParams p) {
@@ -140,7 +145,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    const bool paired = p.cluster == 2;                  // CTA pair sharing one weight stream (non-resident layers)
+    const bool paired = HC_PAIR_WEIGHTS ? p.cluster == 2 : false;      // CTA pair sharing one weight stream (non-resident layers)
     uint32_t crank = 0;
     if (paired) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     // MT = 2: two MMA issuer warps (one per M half), each commits its own MMAs to every barrier the tensor pipe signals
@@ -230,7 +235,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             (void)ns;
             return i + 1;
         };
-        if (p.resident) {
+        if (RES) {
             uint32_t stage = 0;
             for (int ps = 0; ps < p.npass; ++ps)
                 for (int i = 0; i < p.nsteps[ps]; ++stage) i = load_group(steps_s + ps * HC_MAX_STEPS, i, p.nsteps[ps], stage);
@@ -262,7 +267,8 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
         const uint32_t ring16 = (sbase + ring_off) >> 4, wst16 = (uint32_t)p.wst_bytes >> 4;
         const uint32_t halo16 = sbase >> 4, hstride16 = (uint32_t)p.halo_stride >> 4;
         const uint32_t ncol = (uint32_t)p.NCOL;
-        const bool resident = p.resident != 0;
+        constexpr bool resident = RES;              // the whole weight set stays in shared memory: no ring hand-shake in the loop
+        const uint32_t nS = (uint32_t)p.S, nHB = (uint32_t)p.nhb;       // (kept in registers: the loop below is issue-latency bound)
         uint32_t hb = 0, hpar = 0, ws = 0, wpar = 0;
         int it = 0;
         for (long long k = 0, tile = blockIdx.x; k < (paired ? niter : (ntiles - blockIdx.x + G - 1) / G); ++k, tile += G, ++it) {
@@ -275,7 +281,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                     if (fl & ST_GSTART) ptx::mbar_wait(wfull((int)ws), wpar);
                     if (fl & ST_GEND) {
                         if (leader) tc_commit_mc(wempty((int)ws), (uint16_t)3);
-                        if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                        if (++ws == nS) { ws = 0; wpar ^= 1; }
                     }
                 }
                 __syncwarp();
@@ -317,12 +323,12 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
                 if (fl & ST_GEND) {
                     if (!resident) {
                         if (leader) { if (paired) tc_commit_mc(wempty((int)ws), (uint16_t)3); else ptx::tc_commit(wempty((int)ws)); }
-                        if (++ws == (uint32_t)p.S) { ws = 0; wpar ^= 1; }
+                        if (++ws == nS) { ws = 0; wpar ^= 1; }
                     } else ++ws;
                 }
                 if (fl & ST_ENDCHUNK) {
                     if (leader) ptx::tc_commit(hempty((int)hb));
-                    if (++hb == (uint32_t)p.nhb) { hb = 0; hpar ^= 1; }
+                    if (++hb == nHB) { hb = 0; hpar ^= 1; }
                 }
                 st = nx;
             }
@@ -766,32 +772,29 @@ extern "C" int vqb_conv2d_bf16(const void *in, const void *packed, const float *
         if (rc) return rc;
     }
     const int smem = q.nhb * q.halo_stride + q.S * q.wst_bytes + MISC;
-    static int attr_max[2] = {0, 0};
-    if (smem > attr_max[q.MT - 1]) {
-        cudaError_t e = q.MT == 2 ? cudaFuncSetAttribute(hconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                  : cudaFuncSetAttribute(hconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    typedef void (*hconv_fn)(CUtensorMap, CUtensorMap, CUtensorMap, HParams);
+    const int variant = (q.MT - 1) * 2 + (q.resident ? 1 : 0);
+    const hconv_fn fns[4] = {hconv_kernel<1, false>, hconv_kernel<1, true>, hconv_kernel<2, false>, hconv_kernel<2, true>};
+    const hconv_fn fn = fns[variant];
+    static int attr_max[4] = {0, 0, 0, 0};
+    if (smem > attr_max[variant]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr_max[q.MT - 1] = smem;
+        attr_max[variant] = smem;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)(q.ntiles < sms ? q.ntiles : sms);
-    // Streamed weights CAN be shared by CTA pairs (clusters of 2): each CTA loads every other step and multicasts it to both,
-    // halving the L2 -> shared-memory requests per SM; the ring's empty barriers take the commits of both CTAs
-    // (tcgen05.commit multicast), a pair's last CTA may end with a dry iteration.  Parity-green (all bf16 tests incl. the
-    // back-to-back stress), but within box-to-box noise both with one issuer (E3 133 vs 130 us) and with two (E3 117 vs 121,
-    // while the unpaired two-pass layer moved by the same 2-3 % on that box): the weight stream is not the limit.  Off.
-    constexpr bool HC_PAIR_WEIGHTS = false;
+    // Streamed weights CAN be shared by CTA pairs (clusters of 2, -DHC_PAIR_WEIGHTS=1): each CTA loads every other step and
+    // multicasts it to both, halving the L2 -> shared-memory requests per SM; the ring's empty barriers take the commits of
+    // both CTAs (tcgen05.commit multicast), a pair's last CTA may end with a dry iteration.  Parity-green (all bf16 tests incl.
+    // the back-to-back stress), but within box-to-box noise both with one issuer (E3 133 vs 130 us) and with two (E3 117 vs
+    // 121, while the unpaired two-pass layer moved by the same 2-3 % on that box): the weight stream is not the limit.
     q.cluster = (HC_PAIR_WEIGHTS && !q.resident && q.npass == 1 && grid >= 2) ? 2 : 1;
     if (q.cluster == 2) grid &= ~1;
-    cudaError_t le;
-    if (q.cluster == 2)
-        le = q.MT == 2 ? vqb_launch_cluster(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, 2u, tin, tw, twh, q)
-                       : vqb_launch_cluster(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, 2u, tin, tw, twh, q);
-    else
-        le = q.MT == 2 ? vqb_launch(hconv_kernel<2>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q)
-                       : vqb_launch(hconv_kernel<1>, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q);
+    const cudaError_t le = q.cluster == 2 ? vqb_launch_cluster(fn, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, 2u, tin, tw, twh, q)
+                                          : vqb_launch(fn, dim3((unsigned)grid), dim3(HC_THREADS), (size_t)smem, s, tin, tw, twh, q);
     if (le != cudaSuccess) return (int)le;
     VQB_COUNT_LAUNCH(1);
     return vqb_cuda_status(cudaGetLastError());
