@@ -22,11 +22,12 @@
 
 namespace {
 
-constexpr int CIB_THREADS = 512;
+constexpr int CIB_THREADS = 640;        // warps: 0 raw-row producer, 1 MMA, 2 TMEM, 4-11 builders (2 groups), 12-19 epilogue (2 groups)
 constexpr int COUT = 64;
 constexpr uint32_t A_BYTES = 2 * 16384;                 // two K atoms x [128 rows][128 B]
 constexpr uint32_t B_ATOM = COUT * 128;
-constexpr int NA = 3;                                   // im2col tiles / TMEM accumulators / staging tiles in flight
+constexpr int NA = 3;                                   // im2col tiles / TMEM accumulators in flight
+constexpr int NS = 4;                                   // staging tiles: two per epilogue group
 constexpr int NRAW = 4;                                 // staged-input buffers: the TMA loads run three tiles ahead (HBM round trip)
 
 struct CibParams {
@@ -50,7 +51,7 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (sbase - raw);
     // [A x2][B: 2 atoms][staging 16 KB][raw rows x2][barriers, bias]
-    const uint32_t b_off = NA * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + NA * 16384u;
+    const uint32_t b_off = NA * A_BYTES, st_off = b_off + 2 * B_ATOM, raw_off = st_off + NS * 16384u;
     const uint32_t raw_stride = ((uint32_t)p.raw_bytes + 127u) & ~127u;
     const uint32_t bar_off = raw_off + NRAW * raw_stride;
     const uint32_t bars = sbase + bar_off;
@@ -61,8 +62,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
     auto tfull = [&](int s) { return bars + 8u * (2 * NRAW + 2 * NA + s); };
     auto tempty = [&](int s) { return bars + 8u * (2 * NRAW + 3 * NA + s); };
     auto sfree = [&](int s) { return bars + 8u * (2 * NRAW + 4 * NA + s); };
-    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 5 * NA));
-    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 5 * NA + 2));
+    volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 8 * (2 * NRAW + 4 * NA + NS));
+    float *bias_s = reinterpret_cast<float *>(sm + bar_off + 8 * (2 * NRAW + 4 * NA + NS + 2));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.H, W = p.W, OW = W / 2, OH = H / 2, R = p.R, NR = 2 * R + 2;
@@ -72,11 +73,11 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             ptx::mbar_init(afull(s), 4); ptx::mbar_init(aempty(s), 1);
             ptx::mbar_init(tfull(s), 1); ptx::mbar_init(tempty(s), 4);
         }
-        for (int s = 0; s < NA; ++s) ptx::mbar_init(sfree(s), 1);
+        for (int s = 0; s < NS; ++s) ptx::mbar_init(sfree(s), 1);
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&tma_x); ptx::prefetch_tmap(&tma_out);
     }
-    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * NRAW + 5 * NA), 256);
+    if (warp == 2) ptx::tmem_alloc(sbase + bar_off + 8 * (2 * NRAW + 4 * NA + NS), 256);
     for (int c = tid; c < COUT; c += CIB_THREADS) bias_s[c] = p.bias ? __ldg(p.bias + c) : 0.f;
     // ---- B operand, once per CTA: wp[k][co] (k = (r*4+s)*3 + c, 48 rows) -> K-major swizzled rows ----
     for (int i = tid; i < COUT * 12; i += CIB_THREADS) {
@@ -174,10 +175,14 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
         // ===================== epilogue: thread = pixel row; bias, ReLU, bf16, staged tile, one TMA store =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const bool storer = tid == 384;
-        int it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
-            const int s = it % NA;
+        // two groups of four warps take ALTERNATE tiles: an epilogue is one dependent chain per thread (TMEM load -> bias /
+        // ReLU / pack -> staging stores -> proxy fence -> barrier -> TMA store) of about a tile period; each group owns two of
+        // the four staging tiles, so the groups never wait for each other's stores
+        const int eg = (warp - 12) >> 2;
+        const bool storer = tid == 384 + eg * 128;
+        int it = eg;
+        for (long long tile = (long long)blockIdx.x + (long long)eg * G; tile < ntiles; tile += 2LL * G, it += 2) {
+            const int s = it % NA, ss = it % NS;
             ptx::mbar_wait_sleep(tfull(s), (uint32_t)((it / NA) & 1), 32);
             ptx::tc_fence_after();
             float va[32], vb[32];
@@ -189,8 +194,8 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty(s));          // the accumulator is in registers
-            unsigned char *orow = sm + st_off + s * 16384 + row * 128;
-            ptx::mbar_wait(sfree(s), (uint32_t)(((it / NA) & 1) ^ 1));       // the store of tile it-2 has read this staging buffer
+            unsigned char *orow = sm + st_off + ss * 16384 + row * 128;
+            ptx::mbar_wait(sfree(ss), (uint32_t)(((it / NS) & 1) ^ 1));      // this group's store of tile it-4 has read the staging tile
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -208,14 +213,14 @@ conv_in_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
                                    *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
                 }
             ptx::fence_proxy_async();
-            ptx::named_bar_sync(1, 128);
+            ptx::named_bar_sync(1 + eg, 128);
             if (storer) {
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
-                                 "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + st_off + (uint32_t)s * 16384u), "r"(0), "r"((int)(tile * 128)) : "memory");
+                                 "l"(reinterpret_cast<uint64_t>(&tma_out)), "r"(sbase + st_off + (uint32_t)ss * 16384u), "r"(0), "r"((int)(tile * 128)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // release the staging tile of store it-(NA-1): this thread never waits for the store it has just issued
-                asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(NA - 1) : "memory");
-                if (it >= NA - 1) ptx::mbar_arrive(sfree((it - (NA - 1)) % NA));
+                // release the staging tile of this group's PREVIOUS store (tile it-2): never wait for the store just issued
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (it >= 2) ptx::mbar_arrive(sfree((it - 2) % NS));
             }
         }
         if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -258,7 +263,7 @@ int launch_conv_in_bf16_persistent(const float *x, const float *wp, const float 
         if (rc) return rc;
     }
     const int raw_stride = (q.raw_bytes + 127) & ~127;
-    const int smem = NA * (int)A_BYTES + 2 * (int)B_ATOM + NA * 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 5 * NA + 2) + COUT * 4 + 1024;
+    const int smem = NA * (int)A_BYTES + 2 * (int)B_ATOM + NS * 16384 + NRAW * raw_stride + 8 * (2 * NRAW + 4 * NA + NS + 2) + COUT * 4 + 1024;
     if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
     static int attr_max = 0;
     if (smem > attr_max) {
