@@ -48,8 +48,10 @@ extern "C" int vqb_debug_read_res_timeline(unsigned long long *dst, int n) {
 
 namespace {
 
-constexpr int RB_THREADS = 512;       // warps: 0 halo producer, 1 MMA issuer, 2 TMEM + weights, 3 skip producer, 4-11 epilogue 2, 12-15 epilogue 1
-constexpr int RB_NHB = 3;             // halo buffers, rotating over the (tile, chunk) sequence
+constexpr int RB_THREADS = 768;       // warps: 0 halo producer, 1-2 MMA issuers (2: TMEM + weights first), 3 skip producer, 4-11 and 16-23 the
+                                      // two epilogue-2 groups (alternate tiles), 12-15 epilogue 1
+constexpr int RB_NHB = 2;             // halo buffers, rotating over the (tile, chunk) sequence (the third one's 23 KB went to the second
+                                      // staging set; the loads are L2 hits, prefetched two to three tiles ahead)
 constexpr int RB_NISS = 2;            // GEMM1 issuer warps (warp 1: K steps 0-1 of every tap, warp 2: K steps 2-3; private accumulators)
 
 struct ResBfParams {
@@ -81,8 +83,9 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
     const uint32_t w1_step = (uint32_t)Cmid * 128u;                             // one (chunk, tap) weight tile
     const uint32_t w2_off = w1_off + ((9u * chunks * w1_step + 1023u) & ~1023u);
     const uint32_t a2_off = w2_off + (((uint32_t)C * 128u + 1023u) & ~1023u);
-    const uint32_t st_off = a2_off + 16384u;                                    // staging: chunks x [128 px][128 B]
-    const uint32_t bar_off = st_off + (uint32_t)chunks * 16384u;
+    const uint32_t st_off = a2_off + 16384u;                                    // staging: 2 groups x chunks x [128 px][128 B]
+    const uint32_t st_grp = (uint32_t)chunks * 16384u;
+    const uint32_t bar_off = st_off + 2u * st_grp;
     const uint32_t bars = sbase + bar_off;
     auto hfull = [&](int b) { return bars + 8u * b; };
     auto hempty = [&](int b) { return bars + 8u * (3 + b); };
@@ -92,8 +95,8 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
     const uint32_t a2ready = bars + 8u * 11;
     auto d2full = [&](int s) { return bars + 8u * (12 + s); };
     auto d2empty = [&](int s) { return bars + 8u * (14 + s); };
-    auto sfull = [&](int c) { return bars + 8u * (16 + c); };
-    auto sfree = [&](int c) { return bars + 8u * (18 + c); };
+    auto sfull = [&](int g, int c) { return bars + 8u * (16 + 2 * g + c); };      // per epilogue-2 group and 64-channel chunk
+    auto sfree = [&](int g, int c) { return bars + 8u * (20 + 2 * g + c); };
     volatile uint32_t *tmem_holder = reinterpret_cast<volatile uint32_t *>(sm + bar_off + 192);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -104,7 +107,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(d1full(s), RB_NISS); ptx::mbar_init(d1empty(s), 4);
             ptx::mbar_init(d2full(s), 1); ptx::mbar_init(d2empty(s), 8);
-            ptx::mbar_init(sfull(s), 1); ptx::mbar_init(sfree(s), 1);
+            for (int c = 0; c < 2; ++c) { ptx::mbar_init(sfull(s, c), 1); ptx::mbar_init(sfree(s, c), 1); }
         }
         ptx::mbar_init(a2ready, 4);
         ptx::fence_mbar_init();
@@ -170,11 +173,12 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
             for (int c = 0; c < chunks; ++c) {
-                ptx::mbar_wait_sleep(sfree(c), (uint32_t)((it & 1) ^ 1), 100);           // the previous tile's store has read the buffer
+                const int sg = it & 1;                                                   // the epilogue-2 group (and staging set) of this tile
+                ptx::mbar_wait_sleep(sfree(sg, c), (uint32_t)(((it >> 1) & 1) ^ 1), 100);  // that group's previous store has read the buffer
                 if (leader) {
                     if (c == 0) RB_TL(it, 1);
-                    ptx::mbar_expect_tx(sfull(c), 16384u);
-                    tma_load_5d(sbase + st_off + (uint32_t)c * 16384u, &tma_skip, sfull(c), c * 64, gx0, n0, 0, gy0);
+                    ptx::mbar_expect_tx(sfull(sg, c), 16384u);
+                    tma_load_5d(sbase + st_off + (uint32_t)sg * st_grp + (uint32_t)c * 16384u, &tma_skip, sfull(sg, c), c * 64, gx0, n0, 0, gy0);
                 }
             }
         }
@@ -280,7 +284,7 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
                 __syncwarp();
             }
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && warp < 16) {
         // ===================== epilogue 1 (4 warps, one per TMEM lane quadrant): relu(D1) -> A2 =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -316,21 +320,26 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================== epilogue 2 (8 warps): D2 + skip -> ReLU -> bf16, in the staging buffer; TMA store =====================
-        const int q = warp & 3, g = (warp - 4) >> 2;
+        // Two groups of eight warps take ALTERNATE tiles (= one D2 stage and one staging set each).  With one group the
+        // staging buffer carried store(t) -> skip-tile TMA(t+1) -> epilogue(t+1), 0.7k + 1.5k + 1.5k cycles: a whole tile
+        // period (profiles/r02_res_timeline_before.txt).
+        const int eg = warp < 12 ? 0 : 1;
+        const int w8 = warp - (eg ? 16 : 4);
+        const int q = warp & 3, g = w8 >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_t = tmem_base + ((uint32_t)(q * 32) << 16);
         const int cpg = C / 2;                            // columns per warp group (64 or 32)
         const int col0 = g * cpg;
         const int chunk = col0 >> 6;                      // staging buffer (64 channels) this group writes
         const bool storer = (chunks == 2) ? (q == 0 && lane == 0) : (g == 0 && q == 0 && lane == 0);
-        int it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
+        int it = eg;
+        for (long long tile = (long long)blockIdx.x + (long long)eg * G; tile < ntiles; tile += 2LL * G, it += 2) {
             long long t = tile;
             const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
             const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
             const int gx0 = tx * 8, gy0 = ty * p.BH, n0 = (int)t * p.BN;
-            unsigned char *srow = sm + st_off + chunk * 16384 + row * 128;
-            ptx::mbar_wait_sleep(sfull(chunk), (uint32_t)(it & 1), 200);
+            unsigned char *srow = sm + st_off + eg * st_grp + chunk * 16384 + row * 128;
+            ptx::mbar_wait_sleep(sfull(eg, chunk), (uint32_t)((it >> 1) & 1), 200);
             if (tid == 128) RB_TL(it, 10);
             ptx::mbar_wait_sleep(d2full(it & 1), (uint32_t)((it >> 1) & 1), 200);
             ptx::tc_fence_after();
@@ -362,15 +371,15 @@ res_bf16_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(d2empty(it & 1));
             // all warps that wrote this staging buffer are done -> one thread stores it and frees it
-            if (chunks == 2) ptx::named_bar_sync(1 + g, 128);
-            else ptx::named_bar_sync(1, 256);
+            if (chunks == 2) ptx::named_bar_sync(1 + 2 * eg + g, 128);
+            else ptx::named_bar_sync(1 + eg, 256);
             if (storer) {
                 if (tid == 128) RB_TL(it, 12);
-                tma_store_5d(&tma_out, sbase + st_off + (uint32_t)chunk * 16384u, chunk * 64, gx0, n0, 0, gy0);
+                tma_store_5d(&tma_out, sbase + st_off + (uint32_t)eg * st_grp + (uint32_t)chunk * 16384u, chunk * 64, gx0, n0, 0, gy0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 if (tid == 128) RB_TL(it, 13);
-                ptx::mbar_arrive(sfree(chunk));
+                ptx::mbar_arrive(sfree(eg, chunk));
             }
         }
         if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -435,7 +444,7 @@ extern "C" int vqb_residual_layer_bf16(const void *r, const void *w1_packed, con
         if (rc) return rc;
     }
     const int w1_bytes = (9 * q.chunks * Cmid * 128 + 1023) & ~1023, w2_bytes = (C * 128 + 1023) & ~1023;
-    const int smem = RB_NHB * q.halo_stride + w1_bytes + w2_bytes + 16384 + q.chunks * 16384 + 256 + 1024;
+    const int smem = RB_NHB * q.halo_stride + w1_bytes + w2_bytes + 16384 + 2 * q.chunks * 16384 + 256 + 1024;
     if (smem > 227 * 1024) return VQB_ERR_UNSUPPORTED;
     static int attr_max = 0;
     if (smem > attr_max) {
