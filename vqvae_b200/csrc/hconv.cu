@@ -199,7 +199,7 @@ hconv_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__
             tile_origin(tile, gx0, gy0, n0);
             // pull the halo tiles of the tile after next into L2 now: with <= 3 halo buffers the shared-memory load of a
             // tile can only be issued one tile ahead, which does not cover an HBM round trip under full load
-            const long long tpf = tile + 2LL * G;
+            const long long tpf = tile + (p.nchunks >= 4 ? 1LL : 2LL) * G;      // (four-chunk tiles: 166 KB each; two tiles ahead on 148 SMs crowd L2)
             if (leader && tpf < ntiles && (p.npass == 1 || (tpf % p.npass) == 0)) {
                 int px0, py0, pn0;
                 tile_origin(tpf, px0, py0, pn0);
