@@ -187,3 +187,64 @@ def test_reference_checkpoint_loads_on_cpu():
     finally:
         if os.path.exists(out):
             os.remove(out)
+
+
+def test_convt_out_scatter_column_layout():
+    """convt_out_bf16.cu orders the 64 GEMM columns of the output layer by DESTINATION pixel.  Host logic, pinned here:
+    every (ky, kx, co) of the 4x4x3 ConvTranspose2d weight appears exactly once, the 16 pad columns are marked, and the
+    group a column sits in is the one the epilogue reads it from: a tap (ky, kx) of input pixel (y, x) lands on output pixel
+    (2y - 1 + ky, 2x - 1 + kx) (decoder.py:34, k4 s2 p1), i.e. in the 2x2 block of input pixel (y + dy, x + dx) with
+    dy = -1 for ky = 0, +1 for ky = 3, else 0 (same for dx), at block row r = (2y - 1 + ky) - 2(y + dy)."""
+    import ctypes
+    from vqvae_b200 import _lib
+    fn = _lib.lib().vqb_debug_convt_out_scatter_column
+    fn.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
+    seen = {}
+    pads = 0
+    for n in range(64):
+        co, ky, kx = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert fn(n, ctypes.byref(co), ctypes.byref(ky), ctypes.byref(kx)) == 0
+        if co.value < 0:
+            pads += 1
+            continue
+        key = (ky.value, kx.value, co.value)
+        assert key not in seen
+        seen[key] = n
+        dy = -1 if ky.value == 0 else (1 if ky.value == 3 else 0)
+        dx = -1 if kx.value == 0 else (1 if kx.value == 3 else 0)
+        r, s_ = (ky.value - 1) - 2 * dy, (kx.value - 1) - 2 * dx          # position inside the destination's 2x2 block
+        assert r in (0, 1) and s_ in (0, 1)
+        # the column groups the epilogue addresses: own [0,12), up [12,20), down [20,28), left [28,36), right [36,44), corners
+        if (dy, dx) == (0, 0):
+            assert n == (r * 2 + s_) * 3 + co.value
+        elif dx == 0:
+            assert n == (12 if dy == -1 else 20) + s_ * 3 + co.value and r == (1 if dy == -1 else 0)
+        elif dy == 0:
+            assert n == (28 if dx == -1 else 36) + r * 3 + co.value and s_ == (1 if dx == -1 else 0)
+        else:
+            base = {(-1, -1): 44, (-1, 1): 48, (1, -1): 52, (1, 1): 56}[(dy, dx)]
+            assert n == base + co.value and (r, s_) == ((1 if dy == -1 else 0), (1 if dx == -1 else 0))
+    assert len(seen) == 48 and pads == 16
+    assert fn(64, ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int())) != 0
+
+
+def test_bf16_conv_plans_row_counts():
+    """hconv.cu's host-built GEMM step plans (no GPU needed): one packed 128-byte weight row per (output column, tap,
+    64-channel chunk).  Every useful row count follows from the layer: conv Cout x taps x chunks; the stride-2 conv on its
+    space-to-depth view 4 chunks x 4 taps; the stride-2 transposed conv 2 passes x chunks x 2 row taps x (2 Cout + Cout +
+    Cout) columns; the output layer 9 x 16 gather-form rows + the 64 scatter-form columns."""
+    from vqvae_b200 import _lib
+    L = _lib.lib()
+    expect = [
+        (_lib.CONV_K1, 64, 128, 2 * 64),                     # vqvae.py:16
+        (_lib.CONV_K3, 128, 128, 9 * 2 * 128),               # encoder.py:35
+        (_lib.CONV_K3, 32, 128, 9 * 2 * 32),                 # residual.py:20 (W1)
+        (_lib.CONVT_K3, 128, 64, 9 * 128),                   # decoder.py:28
+        (_lib.CONV_K4S2, 128, 64, 4 * 4 * 128),              # encoder.py:32
+        (_lib.CONVT_K4S2, 64, 128, 2 * 2 * 2 * 4 * 64),      # decoder.py:31
+        (_lib.CONVT_K4S2_OUT, 3, 64, 9 * 16 + 64),           # decoder.py:34
+        (_lib.RES_W2, 128, 32, 128),                         # residual.py:23 (W2, Cmid padded to one 64-channel chunk)
+    ]
+    for kind, cout, cin, rows in expect:
+        assert L.vqb_conv_bf16_packed_bytes(kind, cout, cin) == rows * (128 + 16) + 256, (kind, cout, cin)
+    assert L.vqb_conv_bf16_packed_bytes(_lib.CONV_K3, 128, 100) == 0          # Cin must be a multiple of 64: not covered

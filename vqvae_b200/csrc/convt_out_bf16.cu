@@ -229,6 +229,13 @@ void convt_out_scatter_column(int n, int *co, int *ky, int *kx) {
     *co = jj; *ky = (c >> 1) ? 3 : 0; *kx = (c & 1) ? 3 : 0;
 }
 
+// (test hook, tests/test_abi_cpu.py: the column layout is host logic and is pinned without a GPU)
+extern "C" int vqb_debug_convt_out_scatter_column(int n, int *co, int *ky, int *kx) {
+    if (n < 0 || n >= 64 || !co || !ky || !kx) return VQB_ERR_BAD_ARG;
+    convt_out_scatter_column(n, co, ky, kx);
+    return 0;
+}
+
 // in: bf16 NHWC (B, H, W, 64); packed: the layer's packed weights (hconv.cu), GEMM columns of the scatter form at rows
 // [w_row0, w_row0 + 64); out: fp32 NCHW (B, 3, 2H, 2W).
 int launch_convt_out_scatter(const void *in, const void *packed, int packed_rows, int w_row0, const float *bias, float *out, int B, int H,
