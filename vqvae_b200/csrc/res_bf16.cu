@@ -14,10 +14,12 @@
 //          read the skip and wrote the result with one 256-byte row per thread (32 cache lines per warp instruction,
 //          ~8000 LSU wavefronts per 256-pixel tile) and spent 7.7 us per tile against 3 us of MMAs.
 // The MMA issuer software-pipelines across tiles: the first chunk of GEMM1(t+1) is issued before GEMM2(t), so the
-// tensor pipe works while epilogue 1 turns D1(t) into A2(t); D1 and D2 are double buffered in TMEM.
+// tensor pipe works while epilogue 1 turns D1(t) into A2(t); D1 and D2 are double buffered in TMEM.  A second issuer
+// (warp 2) takes K steps 2-3 of every tap into a private accumulator; two epilogue-2 groups (warps 4-11, 16-23) take
+// alternate tiles, each with its own staging set.
 // The layer is HBM-bound at the cfg3 shape (268 MB per application: 41 us at the measured copy peak) and its
-// N = Cmid = 32 MMAs run at 40 cycles instead of the 16-cycle floor (profiles/r02_ubench_mma_rate.txt), which puts the
-// tensor time of a tile (1.5 us at 1.9 GHz) right at its HBM time (1.5 us): both pipes are busy.
+// N = Cmid = 32 MMAs cost ~40 cycles each whoever issues them (4 KB of A per MMA), which puts the tensor time of a tile
+// (2.9k cycles) right at its HBM time: both pipes are busy.  66 us = 62 % of the HBM roofline.
 #include <cstdlib>
 #include <cstring>
 
