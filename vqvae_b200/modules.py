@@ -530,6 +530,11 @@ class VQVAE(nn.Module):
         else:
             x_hat = self.decoder._forward_from_nhwc(zq.view(B, H, W, D), B, H, W)  # :36
         main.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            # the two scalars were allocated in the side stream's pool and are consumed on the caller's stream: without this
+            # their block could be handed out again on the side stream while the caller still reads them
+            embedding_loss.record_stream(main)
+            perplexity.record_stream(main)
         self.last_min_encoding_indices = idx.view(-1, 1)
         if verbose:                                                          # :38-42 (Q8)
             print('original data shape:', x.shape)
